@@ -1,0 +1,418 @@
+// Implicit-GEMM convolution for sm_100a: tcgen05.mma (UMMA) with TMEM accumulators.
+//
+//   D[M = batch*ho*wo][N = cout] = A[M][K = taps*cin] * W[N][K]^T,  fp32 accumulate, 16-bit operands.
+//
+// Persistent, warp-specialised CTA (one per SM, 288 threads):
+//   warps 0-3  producers : gather the im2col A tile (128 pixels x 64 K-elements per stage) with 16-byte
+//                          cp.async straight into the 128B-swizzled K-major layout UMMA reads; the gather
+//                          address math implements zero / reflection padding, stride, nearest x2 upsample
+//                          of source 0 and the channel concat with source 1, so none of those tensors is
+//                          ever materialised (reference: footprints/network.py:124-158).
+//                          Weights (B tile, BN x 64) arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B).
+//   warp  4    MMA issuer: one elected lane issues 4 x tcgen05.mma (M128 x BN x K16) per stage and
+//                          tcgen05.commit's the stage back to the producers / the accumulator to the epilogue.
+//   warps 5-8  epilogue  : tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next tile's
+//                          mainloop overlaps), apply scale/shift (+residual) + activation, store NHWC.
+#include "fp_ptx.cuh"
+#include "fp_internal.h"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace fp {
+
+constexpr int BM = 128;          // output pixels per tile (UMMA M)
+constexpr int BK = 64;           // K elements per stage = one 128-byte swizzle row
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int NUM_PRODUCER_THREADS = 128;
+constexpr int NUM_THREADS = 288;
+constexpr int EPI_FIRST_WARP = 5;
+
+template <int BN>
+struct IgemmCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int LAG = (STAGES >= 6) ? 3 : 2;   // cp.async groups in flight before a stage is published
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator stages, power of two
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) +
+                                    (2 * STAGES + 4) * 8 + 16 + 2 * BN * 4;
+};
+
+struct IgemmParams {
+  const uint8_t* src0;
+  const uint8_t* src1;
+  const uint8_t* w_packed;   // only used when !b_via_tma
+  const float* scale;
+  const float* shift;
+  const uint8_t* residual;
+  void* out;
+  int C0, C1, H0, W0, up0;
+  int Hin, Win;              // virtual input size (after upsample) == source 1 size
+  int cin_log2, taps, KW, stride, pad_t, pad_l, pad_mode;
+  int Ho, Wo, HoWo, M, N;
+  int num_kb, kpad, m_tiles, n_tiles, total_tiles;
+  int act, fmt, out_f32, out_ld, res_ld, b_via_tma;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == FP_ACT_RELU) return fmaxf(x, 0.f);
+  if (act == FP_ACT_ELU) return x > 0.f ? x : expm1f(x);
+  if (act == FP_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
+  return x;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
+  if (fmt == FP_BF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
+  if (fmt == FP_BF16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
+  using Cfg = IgemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int LAG = Cfg::LAG;
+  constexpr int B_STAGE_BYTES = Cfg::B_STAGE_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);   // SWIZZLE_128B needs 1024-B alignment
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(b_smem + STAGES * B_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_scale = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* s_shift = s_scale + BN;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], NUM_PRODUCER_THREADS + (p.b_via_tma ? 1 : 0));
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);
+    }
+    fence_barrier_init();
+    if (p.b_via_tma) tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 4) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 4) {
+    // =============================== PRODUCERS ===============================
+    const int c = tid & 7;    // 16-byte chunk (8 channels) within the 128-byte K row
+    const int r0 = tid >> 3;  // rows r0 + 16*i, i = 0..7
+    const uint32_t a_dst0 = smem_u32(a_smem) + r0 * 128 + ((c ^ (r0 & 7)) << 4);
+    const uint32_t b_dst0 = smem_u32(b_smem) + r0 * 128 + ((c ^ (r0 & 7)) << 4);
+    const int Cin = p.C0 + p.C1;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      // per-row output pixel -> (image, y0, x0) of the top-left tap in virtual input coordinates
+      int row_img[8], row_yx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m_tile * BM + r0 + 16 * i;
+        if (m < p.M) {
+          const int n = m / p.HoWo;
+          const int rem = m - n * p.HoWo;
+          const int oy = rem / p.Wo;
+          const int ox = rem - oy * p.Wo;
+          row_img[i] = n;
+          row_yx[i] = ((oy * p.stride - p.pad_t + 64) << 16) | (ox * p.stride - p.pad_l + 64);
+        } else {
+          row_img[i] = -1;
+          row_yx[i] = 0;
+        }
+      }
+      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, 1);
+        if (p.b_via_tma) {
+          if (tid == 0) {
+            mbar_arrive_expect_tx(&full_bar[s], B_STAGE_BYTES);
+            tma_load_2d(smem_u32(b_smem) + s * B_STAGE_BYTES, &tmap_w, &full_bar[s], kb * BK, n_tile * BN);
+          }
+        } else {
+          const uint8_t* wsrc = p.w_packed + (static_cast<size_t>(n_tile) * BN * p.kpad + kb * BK + c * 8) * 2;
+#pragma unroll
+          for (int i = 0; i < BN / 16; ++i) {
+            const int r = r0 + 16 * i;
+            cp_async_16(b_dst0 + s * B_STAGE_BYTES + i * 2048, wsrc + static_cast<size_t>(r) * p.kpad * 2, 16);
+          }
+        }
+        // which tap / channel slice does this thread's chunk belong to in this K block?
+        const int ch0 = (kb * 8 + c) * 8;
+        const int tap = ch0 >> p.cin_log2;
+        int cc = ch0 & (Cin - 1);
+        const bool k_ok = tap < p.taps;
+        const int th = tap / p.KW;
+        const int tw = tap - th * p.KW;
+        const uint8_t* sbase;
+        int Cs, Hs, Ws, up;
+        if (cc < p.C0) {
+          sbase = p.src0; Cs = p.C0; Hs = p.H0; Ws = p.W0; up = p.up0;
+        } else {
+          sbase = p.src1; cc -= p.C0; Cs = p.C1; Hs = p.Hin; Ws = p.Win; up = 0;
+        }
+        const uint32_t dst = a_dst0 + s * A_STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int iy = (row_yx[i] >> 16) - 64 + th;
+          int ix = (row_yx[i] & 0xFFFF) - 64 + tw;
+          bool ok = k_ok && (row_img[i] >= 0);
+          if (p.pad_mode == FP_PAD_REFLECT) {
+            iy = iy < 0 ? -iy : (iy >= p.Hin ? 2 * p.Hin - 2 - iy : iy);
+            ix = ix < 0 ? -ix : (ix >= p.Win ? 2 * p.Win - 2 - ix : ix);
+          } else {
+            ok = ok && (static_cast<unsigned>(iy) < static_cast<unsigned>(p.Hin)) &&
+                 (static_cast<unsigned>(ix) < static_cast<unsigned>(p.Win));
+          }
+          if (up) { iy >>= 1; ix >>= 1; }
+          const size_t off = ok ? ((static_cast<size_t>(row_img[i]) * Hs + iy) * Ws + ix) * Cs + cc : 0;
+          cp_async_16(dst + i * 2048, sbase + off * 2, ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (it >= static_cast<uint32_t>(LAG)) {
+          cp_async_wait<LAG>();
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[(it - LAG) % STAGES]);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    for (uint32_t j = (it >= static_cast<uint32_t>(LAG) ? it - LAG : 0u); j < it; ++j) mbar_arrive(&full_bar[j % STAGES]);
+  } else if (warp == 4) {
+    // =============================== MMA ISSUER ===============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(BM, BN, p.fmt, p.fmt, 0, 0);
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t acc = ti & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1, 2);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1, 3);
+          tcgen05_fence_after();
+          const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(a_smem) + s * A_STAGE_BYTES, 16, 1024);
+          const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(b_smem) + s * B_STAGE_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advancing 16 K-elements = 32 bytes inside the swizzle row = +2 in the (addr >> 4) field
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== EPILOGUE ===============================
+    const int q = warp & 3;            // TMEM lane quadrant this warp is allowed to read
+    const int row = q * 32 + lane;
+    const int e = tid - EPI_FIRST_WARP * 32;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const uint32_t acc = ti & 1;
+      named_bar_sync(1, 128);          // everyone finished reading the previous tile's scale/shift
+      for (int j = e; j < BN; j += 128) {
+        const int n = n_tile * BN + j;
+        s_scale[j] = (p.scale != nullptr && n < p.N) ? p.scale[n] : 1.f;
+        s_shift[j] = (p.shift != nullptr && n < p.N) ? p.shift[n] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1, 4);
+      tcgen05_fence_after();
+      const int m = m_tile * BM + row;
+      const bool m_ok = m < p.M;
+      constexpr int CW = (BN >= 32) ? 32 : 16;
+#pragma unroll 1
+      for (int j = 0; j < BN; j += CW) {
+        uint32_t v[CW];
+        const uint32_t taddr = tmem_base + acc * BN + j + (static_cast<uint32_t>(q * 32) << 16);
+        if constexpr (CW == 32) tmem_ld_32x32b_x32(taddr, v); else tmem_ld_32x32b_x16(taddr, v);
+        tmem_ld_wait();
+        const int n0 = n_tile * BN + j;
+        if (m_ok && n0 < p.N) {
+          float f[CW];
+#pragma unroll
+          for (int x = 0; x < CW; ++x) f[x] = __uint_as_float(v[x]) * s_scale[j + x] + s_shift[j + x];
+          const int ncols = min(CW, p.N - n0);
+          if (p.residual != nullptr) {
+            const uint8_t* rp = p.residual + (static_cast<size_t>(m) * p.res_ld + n0) * 2;
+            if (ncols == CW) {
+#pragma unroll
+              for (int x = 0; x < CW / 8; ++x) {
+                const uint4 r = *reinterpret_cast<const uint4*>(rp + x * 16);
+                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                  const float2 t = unpack2(rr[y], p.fmt);
+                  f[x * 8 + 2 * y] += t.x;
+                  f[x * 8 + 2 * y + 1] += t.y;
+                }
+              }
+            } else {
+              for (int x = 0; x < ncols; ++x) {
+                const uint16_t h = *reinterpret_cast<const uint16_t*>(rp + x * 2);
+                f[x] += unpack2(h, p.fmt).x;
+              }
+            }
+          }
+#pragma unroll
+          for (int x = 0; x < CW; ++x) f[x] = apply_act(f[x], p.act);
+          if (p.out_f32) {
+            float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + n0;
+            if (ncols == CW && (p.out_ld & 3) == 0) {
+#pragma unroll
+              for (int x = 0; x < CW / 4; ++x)
+                *reinterpret_cast<float4*>(op + 4 * x) = make_float4(f[4 * x], f[4 * x + 1], f[4 * x + 2], f[4 * x + 3]);
+            } else {
+#pragma unroll
+              for (int x = 0; x < CW; ++x) if (x < ncols) op[x] = f[x];
+            }
+          } else {
+            uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (static_cast<size_t>(m) * p.out_ld + n0) * 2;
+            if (ncols == CW && (p.out_ld & 7) == 0) {
+#pragma unroll
+              for (int x = 0; x < CW / 8; ++x) {
+                uint4 o;
+                o.x = pack2(f[8 * x], f[8 * x + 1], p.fmt);
+                o.y = pack2(f[8 * x + 2], f[8 * x + 3], p.fmt);
+                o.z = pack2(f[8 * x + 4], f[8 * x + 5], p.fmt);
+                o.w = pack2(f[8 * x + 6], f[8 * x + 7], p.fmt);
+                *reinterpret_cast<uint4*>(op + 16 * x) = o;
+              }
+            } else {
+#pragma unroll
+              for (int x = 0; x < CW; ++x)
+                if (x < ncols) *reinterpret_cast<uint16_t*>(op + 2 * x) = static_cast<uint16_t>(pack2(f[x], 0.f, p.fmt) & 0xFFFF);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------------
+template <int BN>
+static int launch_igemm(const IgemmParams& p, const CUtensorMap& tmap, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = conv_igemm_kernel<BN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p, tmap);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "conv_igemm launch (BN=%d): %s", BN, cudaGetErrorString(e));
+  return FP_OK;
+}
+
+static int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return (1 << l) == v ? l : -1;
+}
+
+}  // namespace fp
+
+using namespace fp;
+
+extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* src1, const void* w_packed,
+                           const float* scale, const float* shift, const void* residual, void* out, void* stream) {
+  if (d == nullptr || src0 == nullptr || w_packed == nullptr || out == nullptr)
+    return set_error(FP_ERR_ARG, "fp_conv_fwd: null argument");
+  const int cin = d->c0 + d->c1;
+  const int cl2 = ilog2_exact(cin);
+  if (cl2 < 3) return set_error(FP_ERR_ARG, "fp_conv_fwd: c0+c1=%d must be a power of two >= 8", cin);
+  if ((d->c0 & 7) || (d->c1 & 7)) return set_error(FP_ERR_ARG, "fp_conv_fwd: channel counts must be multiples of 8");
+  if (d->c1 > 0 && src1 == nullptr) return set_error(FP_ERR_ARG, "fp_conv_fwd: src1 is null but c1=%d", d->c1);
+  if (d->kpad % 64 || d->kpad < d->kh * d->kw * cin) return set_error(FP_ERR_ARG, "fp_conv_fwd: bad kpad %d", d->kpad);
+  if (d->npad % d->bn || d->npad < d->cout) return set_error(FP_ERR_ARG, "fp_conv_fwd: bad npad %d (bn %d, cout %d)", d->npad, d->bn, d->cout);
+  if (d->dtype != FP_F16 && d->dtype != FP_BF16) return set_error(FP_ERR_ARG, "fp_conv_fwd: bad dtype");
+  const int Hin = d->up0 ? 2 * d->h0 : d->h0, Win = d->up0 ? 2 * d->w0 : d->w0;
+  if (d->pad_mode == FP_PAD_REFLECT && (d->pad_t > 1 || d->pad_l > 1 || Hin < 2 || Win < 2 || d->kh > 3 || d->kw > 3))
+    return set_error(FP_ERR_UNSUPPORTED, "fp_conv_fwd: reflection padding is implemented for pad 1, 3x3 only");
+  if (Hin * d->stride + 64 >= 65536 || Win * d->stride + 64 >= 65536 || d->batch <= 0)
+    return set_error(FP_ERR_UNSUPPORTED, "fp_conv_fwd: spatial size too large");
+  int rc = fp_check_device();
+  if (rc != FP_OK) return rc;
+
+  IgemmParams p{};
+  p.src0 = static_cast<const uint8_t*>(src0);
+  p.src1 = static_cast<const uint8_t*>(src1);
+  p.w_packed = static_cast<const uint8_t*>(w_packed);
+  p.scale = scale; p.shift = shift;
+  p.residual = static_cast<const uint8_t*>(residual);
+  p.out = out;
+  p.C0 = d->c0; p.C1 = d->c1; p.H0 = d->h0; p.W0 = d->w0; p.up0 = d->up0;
+  p.Hin = Hin; p.Win = Win;
+  p.cin_log2 = cl2; p.taps = d->kh * d->kw; p.KW = d->kw; p.stride = d->stride;
+  p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.pad_mode = d->pad_mode;
+  p.Ho = d->ho; p.Wo = d->wo; p.HoWo = d->ho * d->wo; p.M = d->batch * d->ho * d->wo; p.N = d->cout;
+  p.num_kb = d->kpad / 64; p.kpad = d->kpad;
+  p.m_tiles = (p.M + BM - 1) / BM; p.n_tiles = d->npad / d->bn; p.total_tiles = p.m_tiles * p.n_tiles;
+  p.act = d->act; p.fmt = d->dtype; p.out_f32 = d->out_f32; p.out_ld = d->out_ld; p.res_ld = d->res_ld;
+  p.b_via_tma = d->b_via_tma;
+
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (d->b_via_tma) {
+    rc = make_tmap_2d_sw128(&tmap, w_packed, static_cast<uint64_t>(d->kpad), static_cast<uint64_t>(d->npad), 64u,
+                            static_cast<uint32_t>(d->bn));
+    if (rc != FP_OK) return rc;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (d->bn) {
+    case 16: return launch_igemm<16>(p, tmap, st);
+    case 32: return launch_igemm<32>(p, tmap, st);
+    case 64: return launch_igemm<64>(p, tmap, st);
+    case 128: return launch_igemm<128>(p, tmap, st);
+    case 256: return launch_igemm<256>(p, tmap, st);
+    default: return set_error(FP_ERR_ARG, "fp_conv_fwd: bn=%d not in {16,32,64,128,256}", d->bn);
+  }
+}

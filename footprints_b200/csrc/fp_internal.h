@@ -1,0 +1,25 @@
+// Internal host-side helpers shared by the translation units of libfootprints_b200.so.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/footprints_b200.h"
+
+namespace fp {
+
+// printf-style thread-local error message; returns `code` so callers can `return set_error(...)`.
+int set_error(int code, const char* fmt, ...);
+int num_sms();
+// 2-D row-major 16-bit matrix [rows][cols] -> tensor map with box {box_cols, box_rows}, SWIZZLE_128B.
+int make_tmap_2d_sw128(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
+                       uint32_t box_rows);
+
+#define FP_CHECK_LAUNCH(name)                                                                  \
+  do {                                                                                         \
+    cudaError_t e__ = cudaGetLastError();                                                      \
+    if (e__ != cudaSuccess) return fp::set_error(FP_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+}  // namespace fp

@@ -1,0 +1,101 @@
+/* footprints_b200 — C ABI of the B200 (sm_100a) kernels behind the Footprints encoder-decoder.
+ *
+ * The reference (nianticlabs/footprints) has no FFI layer: its device work is PyTorch library calls
+ * issued from footprints/network.py, footprints/training/losses.py and torch.optim.Adam.  Each entry
+ * point below replaces the library calls of the cited reference lines (paths relative to the
+ * reference checkout).  The Python host in footprints_b200/ binds these with ctypes
+ * (footprints_b200/_lib.py); INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - POD arguments only; every pointer is a device pointer owned by the caller (PyTorch allocator);
+ *     the library never allocates, frees or retains device memory.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *   - Return 0 on success, a negative FP_ERR_* otherwise; fp_last_error() gives a thread-local
+ *     message.  Nothing throws or aborts.  There is no CPU fallback: without an sm_100 device the
+ *     launch functions return FP_ERR_CUDA / FP_ERR_ARCH.
+ *   - Activations are NHWC, 16-bit (FP_F16 or FP_BF16); accumulation is fp32 in TMEM.
+ */
+#ifndef FOOTPRINTS_B200_H
+#define FOOTPRINTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FP_VERSION 100
+
+enum { FP_OK = 0, FP_ERR_ARG = -1, FP_ERR_CUDA = -2, FP_ERR_ARCH = -3, FP_ERR_UNSUPPORTED = -4 };
+enum { FP_F16 = 0, FP_BF16 = 1 };
+enum { FP_ACT_NONE = 0, FP_ACT_RELU = 1, FP_ACT_ELU = 2, FP_ACT_SIGMOID = 3 };
+enum { FP_PAD_ZERO = 0, FP_PAD_REFLECT = 1 };
+
+int fp_version(void);
+const char* fp_last_error(void);
+/* 0 if the current device is sm_100 (B200); FP_ERR_ARCH / FP_ERR_CUDA otherwise. */
+int fp_check_device(void);
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores: M = batch*ho*wo output pixels, N = cout,
+ * K = kh*kw*(c0+c1).  The A operand is gathered on the fly from up to two NHWC sources, which
+ * implements without materialising anything:
+ *   - zero padding (torchvision resnet.py conv3x3/conv1x1, footprints/network.py:40-44),
+ *   - ReflectionPad2d(1) (footprints/network.py:115,126,132,167,175),
+ *   - F.interpolate(scale_factor=2, mode='nearest') of source 0 (network.py:98,154),
+ *   - torch.cat([x, skip], 1) (network.py:155): channels [0,c0) from src0, [c0,c0+c1) from src1.
+ * Epilogue: y = act(acc*scale[n] + shift[n] (+ residual[m][n])), i.e. folded eval-mode BatchNorm
+ * + ReLU + residual add (resnet.py:92-104) or bias + ELU (network.py:127-136) or bias (+Sigmoid)
+ * for the heads (network.py:176-178). */
+typedef struct FpConvDesc {
+  int32_t batch;
+  int32_t c0, h0, w0; /* source 0: channels, stored height/width                                  */
+  int32_t up0;        /* 1: source 0 is nearest-upsampled x2 (virtual input = 2*h0 x 2*w0)        */
+  int32_t c1;         /* source 1 channels (0 = no concat); stored at the virtual input size      */
+  int32_t kh, kw, stride, pad_t, pad_l;
+  int32_t pad_mode;   /* FP_PAD_ZERO / FP_PAD_REFLECT                                             */
+  int32_t ho, wo;     /* output height/width                                                      */
+  int32_t cout;       /* valid output channels                                                    */
+  int32_t kpad;       /* packed K (multiple of 64, >= kh*kw*(c0+c1))                              */
+  int32_t npad;       /* packed weight rows (multiple of bn, >= cout)                             */
+  int32_t bn;         /* N tile: 16, 32, 64, 128 or 256                                           */
+  int32_t act;        /* FP_ACT_*                                                                 */
+  int32_t dtype;      /* FP_F16 / FP_BF16 for sources, weights, residual and 16-bit output        */
+  int32_t out_f32;    /* 1: write fp32 rows instead of 16-bit                                     */
+  int32_t out_ld;     /* output row stride in elements                                            */
+  int32_t res_ld;     /* residual row stride in elements                                          */
+  int32_t b_via_tma;  /* 1: weights by TMA (default); 0: weights by cp.async (debug)              */
+} FpConvDesc;
+
+int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* src1, const void* w_packed,
+                const float* scale, const float* shift, const void* residual, void* out, void* stream);
+
+/* OIHW fp32 -> packed [npad][kpad] 16-bit, K index = (ky*kw + kx)*cin + c (tap-major, channel-minor),
+ * zero padded.  flip=1 packs the dgrad operand instead: rows = cin, K = (ky*kw+kx)*cout + co with the
+ * filter rotated by 180 degrees.  Replaces nothing in the reference (weights there stay OIHW fp32 for
+ * cuDNN); it is the layout the UMMA descriptors of fp_conv_fwd expect. */
+int fp_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int npad, int kpad, int dtype,
+                        int flip, void* w_packed, void* stream);
+
+/* Stem weight [64][3][7][7] -> packed [npad][256] for the space-to-depth formulation: the 7x7/2 conv
+ * (torchvision resnet.py:197) equals a 4x4/1 conv over 2x2 space-to-depth blocks of 16 channels
+ * ((dy*2+dx)*4 + c, c<3). */
+int fp_pack_stem_weight(const float* w_oihw, int cout, int npad, int dtype, void* w_packed, void* stream);
+
+/* image NCHW fp32 in [0,1] -> (x-0.45)/0.225 (footprints/network.py:50) -> space-to-depth NHWC
+ * [batch][h/2][w/2][16] 16-bit. */
+int fp_stem_prep(const float* image_nchw, int batch, int h, int w, int dtype, void* out_s2d, void* stream);
+
+/* MaxPool2d(3, stride 2, pad 1) on NHWC 16-bit (torchvision resnet.py:200 via network.py:41). */
+int fp_maxpool3x3s2(const void* in, int batch, int h, int w, int c, int dtype, void* out, void* stream);
+
+/* Heads: bilinear upsample (align_corners=False, integer scale; network.py:180-181) of the two decoders'
+ * [batch][h][w][2] fp32 head maps into one NCHW fp32 [batch][4][h*scale][w*scale] tensor
+ * (torch.cat([mask, depth], 1), network.py:27-28).  scale 1 is a plain layout change. */
+int fp_heads_to_nchw(const float* mask_head, const float* depth_head, int batch, int h, int w, int scale,
+                     float* out_nchw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOOTPRINTS_B200_H */
