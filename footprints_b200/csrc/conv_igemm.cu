@@ -2,16 +2,16 @@
 //
 //   D[M = batch*ho*wo][N = cout] = A[M][K = taps*cin] * W[N][K]^T,  fp32 accumulate, 16-bit operands.
 //
-// Persistent, warp-specialised CTA (one per SM, 288 threads):
-//   warps 0-3  producers : gather the im2col A tile (128 pixels x 64 K-elements per stage) with 16-byte
-//                          cp.async straight into the 128B-swizzled K-major layout UMMA reads; the gather
-//                          address math implements zero / reflection padding, stride, nearest x2 upsample
-//                          of source 0 and the channel concat with source 1, so none of those tensors is
-//                          ever materialised (reference: footprints/network.py:124-158).
+// Persistent, warp-specialised CTA (one per SM, 544 threads):
+//   warps 0-7  producers : gather the im2col A tile (128 pixels x 64 K-elements per stage) with 16-byte
+//                          cp.async straight into the 128B-swizzled K-major layout UMMA reads; per-row
+//                          tap tables (make_row_info) implement zero / reflection padding, stride, the
+//                          nearest x2 upsample of source 0 and the channel concat with source 1, so none
+//                          of those tensors is ever materialised (reference: footprints/network.py:124-158).
 //                          Weights (B tile, BN x 64) arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B).
-//   warp  4    MMA issuer: one elected lane issues 4 x tcgen05.mma (M128 x BN x K16) per stage and
+//   warp  8    MMA issuer: one elected lane issues 4 x tcgen05.mma (M128 x BN x K16) per stage and
 //                          tcgen05.commit's the stage back to the producers / the accumulator to the epilogue.
-//   warps 5-8  epilogue  : tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next tile's
+//   warps 9-16 epilogue  : tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next tile's
 //                          mainloop overlaps), apply scale/shift (+residual) + activation, store NHWC.
 #include "fp_ptx.cuh"
 #include "fp_internal.h"
@@ -24,18 +24,23 @@ namespace fp {
 constexpr int BM = 128;          // output pixels per tile (UMMA M)
 constexpr int BK = 64;           // K elements per stage = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
-constexpr int NUM_PRODUCER_THREADS = 128;
-constexpr int NUM_THREADS = 288;
-constexpr int EPI_FIRST_WARP = 5;
+constexpr int NUM_PRODUCER_WARPS = 8;
+constexpr int NUM_PRODUCER_THREADS = NUM_PRODUCER_WARPS * 32;
+constexpr int MMA_WARP = NUM_PRODUCER_WARPS;
+constexpr int EPI_FIRST_WARP = MMA_WARP + 1;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
+constexpr int NUM_THREADS = (EPI_FIRST_WARP + NUM_EPI_WARPS) * 32;   // 544
+constexpr int ROWS_PER_THREAD = BM / (NUM_PRODUCER_THREADS / 8);     // 4
+constexpr int KTAB_ENTRIES = 1024;   // one entry per 16-byte K chunk: kpad <= 8192
 
 template <int BN>
 struct IgemmCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int LAG = (STAGES >= 6) ? 3 : 2;   // cp.async groups in flight before a stage is published
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator stages, power of two
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) +
-                                    (2 * STAGES + 4) * 8 + 16 + 2 * BN * 4;
+                                    (2 * STAGES + 4) * 8 + 16 + 2 * BN * 4 + 2 * BM * 16 + KTAB_ENTRIES * 4;
 };
 
 struct IgemmParams {
@@ -48,16 +53,22 @@ struct IgemmParams {
   void* out;
   int C0, C1, H0, W0, up0;
   int Hin, Win;              // virtual input size (after upsample) == source 1 size
-  int cin_log2, taps, KW, stride, pad_t, pad_l, pad_mode;
+  int cin_log2, taps, KH, KW, stride, pad_t, pad_l, pad_mode;
   int Ho, Wo, HoWo, M, N;
   int num_kb, kpad, m_tiles, n_tiles, total_tiles;
   int act, fmt, out_f32, out_ld, res_ld, b_via_tma;
 };
 
+// ELU(alpha=1) negative branch: expm1 via a short Taylor series near 0 and ex2.approx elsewhere
+// (abs error < 1e-7, far below the 16-bit output rounding).
+__device__ __forceinline__ float fast_expm1_neg(float x) {
+  const float poly = x * (1.f + x * (0.5f + x * (0.16666667f + x * 0.041666668f)));
+  return x > -0.125f ? poly : __expf(x) - 1.f;
+}
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == FP_ACT_RELU) return fmaxf(x, 0.f);
-  if (act == FP_ACT_ELU) return x > 0.f ? x : expm1f(x);
-  if (act == FP_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
+  if (act == FP_ACT_ELU) return x > 0.f ? x : fast_expm1_neg(x);
+  if (act == FP_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
   return x;
 }
 
@@ -74,12 +85,39 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
+// Per output row and per source: element offset of the reference source pixel (the first in-range tap)
+// plus 4-bit per-tap row/column deltas relative to it (15 = tap reads padding zeros).  Encodes zero and
+// reflection padding, stride, and the nearest x2 upsample; the K loop then needs ~10 instructions per
+// 16-byte cp.async instead of re-deriving the mapping.
+__device__ __forceinline__ void make_row_info(int n, int y0, int x0, int Hv, int Wv, int up, int Hs, int Ws, int Cs,
+                                              int KH, int KW, int reflect, uint32_t& base, uint32_t& code) {
+  const int refy = max(y0, 0) >> up, refx = max(x0, 0) >> up;
+  base = static_cast<uint32_t>(((n * Hs + refy) * Ws + refx) * Cs);
+  uint32_t cd = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    int vy = y0 + t, vx = x0 + t;
+    bool oky = t < KH, okx = t < KW;
+    if (reflect) {
+      vy = vy < 0 ? -vy : (vy >= Hv ? 2 * Hv - 2 - vy : vy);
+      vx = vx < 0 ? -vx : (vx >= Wv ? 2 * Wv - 2 - vx : vx);
+    } else {
+      oky = oky && static_cast<unsigned>(vy) < static_cast<unsigned>(Hv);
+      okx = okx && static_cast<unsigned>(vx) < static_cast<unsigned>(Wv);
+    }
+    const uint32_t dy = oky ? static_cast<uint32_t>((vy >> up) - refy) : 15u;
+    const uint32_t dx = okx ? static_cast<uint32_t>((vx >> up) - refx) : 15u;
+    cd |= (dy & 15u) << (4 * t);
+    cd |= (dx & 15u) << (16 + 4 * t);
+  }
+  code = cd;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
   using Cfg = IgemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int LAG = Cfg::LAG;
   constexpr int B_STAGE_BYTES = Cfg::B_STAGE_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -94,6 +132,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* s_scale = reinterpret_cast<float*>(tmem_ptr_smem + 4);
   float* s_shift = s_scale + BN;
+  uint4* s_rowinfo = reinterpret_cast<uint4*>(s_shift + BN);   // [2][BM] {base0, code0, base1, code1}
+  uint32_t* s_ktab = reinterpret_cast<uint32_t*>(s_rowinfo + 2 * BM);   // per 16-byte K chunk: tap/channel decode
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -101,54 +141,72 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], NUM_PRODUCER_THREADS + (p.b_via_tma ? 1 : 0));
+      mbar_init(&full_bar[s], NUM_PRODUCER_THREADS + (p.b_via_tma ? 1 : 0));   // one async arrive per producer thread
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);
+      mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
     }
     fence_barrier_init();
     if (p.b_via_tma) tma_prefetch_desc(&tmap_w);
   }
-  if (warp == 4) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+  if (warp == MMA_WARP) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+  // K-chunk table: chunk j covers channels [8j, 8j+8) of the tap-major K axis.  Entry bits:
+  //   [0,5) row-code shift (4*th)   [5,10) col-code shift (16+4*tw)   bit 10 source 1   bit 11 chunk is K padding
+  //   [12,32) channel offset inside the source pixel
+  for (int j = tid; j < p.num_kb * 8; j += NUM_THREADS) {
+    const int ch0 = j * 8;
+    const int tap = ch0 >> p.cin_log2;
+    int cc = ch0 & ((p.C0 + p.C1) - 1);
+    const int th = tap / p.KW, tw = tap - th * p.KW;
+    const uint32_t second = cc >= p.C0 ? 1u : 0u;
+    if (second) cc -= p.C0;
+    const uint32_t pad = tap >= p.taps ? 1u : 0u;
+    s_ktab[j] = pad ? (1u << 11) : (static_cast<uint32_t>(4 * th) | (static_cast<uint32_t>(16 + 4 * tw) << 5) | (second << 10) |
+                                     (static_cast<uint32_t>(cc) << 12));
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp < 4) {
+  if (warp < NUM_PRODUCER_WARPS) {
     // =============================== PRODUCERS ===============================
     const int c = tid & 7;    // 16-byte chunk (8 channels) within the 128-byte K row
-    const int r0 = tid >> 3;  // rows r0 + 16*i, i = 0..7
-    const uint32_t a_dst0 = smem_u32(a_smem) + r0 * 128 + ((c ^ (r0 & 7)) << 4);
-    const uint32_t b_dst0 = smem_u32(b_smem) + r0 * 128 + ((c ^ (r0 & 7)) << 4);
-    const int Cin = p.C0 + p.C1;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int r0 = tid >> 3;  // rows r0 + 32*i, i = 0..3
+    const uint32_t swz = static_cast<uint32_t>(r0 * 128 + ((c ^ (r0 & 7)) << 4));
+    const uint32_t a_dst0 = smem_u32(a_smem) + swz;
+    const uint32_t b_dst0 = smem_u32(b_smem) + swz;
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
-      // per-row output pixel -> (image, y0, x0) of the top-left tap in virtual input coordinates
-      int row_img[8], row_yx[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m_tile * BM + r0 + 16 * i;
+      uint4* info_buf = s_rowinfo + (ti & 1) * BM;
+      if (tid < BM) {
+        const int m = m_tile * BM + tid;
+        uint4 ri = make_uint4(0u, 0xFFFFFFFFu, 0u, 0xFFFFFFFFu);
         if (m < p.M) {
           const int n = m / p.HoWo;
           const int rem = m - n * p.HoWo;
           const int oy = rem / p.Wo;
           const int ox = rem - oy * p.Wo;
-          row_img[i] = n;
-          row_yx[i] = ((oy * p.stride - p.pad_t + 64) << 16) | (ox * p.stride - p.pad_l + 64);
-        } else {
-          row_img[i] = -1;
-          row_yx[i] = 0;
+          const int y0 = oy * p.stride - p.pad_t, x0 = ox * p.stride - p.pad_l;
+          make_row_info(n, y0, x0, p.Hin, p.Win, p.up0, p.H0, p.W0, p.C0, p.KH, p.KW, p.pad_mode, ri.x, ri.y);
+          if (p.C1 > 0) make_row_info(n, y0, x0, p.Hin, p.Win, 0, p.Hin, p.Win, p.C1, p.KH, p.KW, p.pad_mode, ri.z, ri.w);
         }
+        info_buf[tid] = ri;
       }
+      named_bar_sync(2, NUM_PRODUCER_THREADS);
+      uint4 info[ROWS_PER_THREAD];
+#pragma unroll
+      for (int i = 0; i < ROWS_PER_THREAD; ++i) info[i] = info_buf[r0 + 32 * i];
+
       for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1, 1);
+        if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1, 1);
+        __syncwarp();
         if (p.b_via_tma) {
           if (tid == 0) {
             mbar_arrive_expect_tx(&full_bar[s], B_STAGE_BYTES);
@@ -157,54 +215,34 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
         } else {
           const uint8_t* wsrc = p.w_packed + (static_cast<size_t>(n_tile) * BN * p.kpad + kb * BK + c * 8) * 2;
 #pragma unroll
-          for (int i = 0; i < BN / 16; ++i) {
-            const int r = r0 + 16 * i;
-            cp_async_16(b_dst0 + s * B_STAGE_BYTES + i * 2048, wsrc + static_cast<size_t>(r) * p.kpad * 2, 16);
+          for (int i = 0; i < (BN + 31) / 32; ++i) {
+            const int r = r0 + 32 * i;
+            if (r < BN) cp_async_16(b_dst0 + s * B_STAGE_BYTES + i * 4096, wsrc + static_cast<size_t>(r) * p.kpad * 2, 16);
           }
         }
-        // which tap / channel slice does this thread's chunk belong to in this K block?
-        const int ch0 = (kb * 8 + c) * 8;
-        const int tap = ch0 >> p.cin_log2;
-        int cc = ch0 & (Cin - 1);
-        const bool k_ok = tap < p.taps;
-        const int th = tap / p.KW;
-        const int tw = tap - th * p.KW;
-        const uint8_t* sbase;
-        int Cs, Hs, Ws, up;
-        if (cc < p.C0) {
-          sbase = p.src0; Cs = p.C0; Hs = p.H0; Ws = p.W0; up = p.up0;
-        } else {
-          sbase = p.src1; cc -= p.C0; Cs = p.C1; Hs = p.Hin; Ws = p.Win; up = 0;
-        }
+        // decode this thread's K chunk (tap, channel slice, source) from the table built at kernel start
+        const uint32_t ke = s_ktab[kb * 8 + c];
+        const bool second = (ke & (1u << 10)) != 0u;
+        const uint32_t padmask = (ke >> 8) & 8u;                             // bit 11 -> 8: forces "invalid"
+        const uint32_t shy = ke & 31u, shx = (ke >> 5) & 31u, cc = ke >> 12;
+        const uint8_t* sbase = second ? p.src1 : p.src0;
+        const uint32_t pstride = second ? p.C1 : p.C0;                       // elements per source pixel
+        const uint32_t rstride = second ? p.Win * p.C1 : p.W0 * p.C0;        // elements per source row
         const uint32_t dst = a_dst0 + s * A_STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          int iy = (row_yx[i] >> 16) - 64 + th;
-          int ix = (row_yx[i] & 0xFFFF) - 64 + tw;
-          bool ok = k_ok && (row_img[i] >= 0);
-          if (p.pad_mode == FP_PAD_REFLECT) {
-            iy = iy < 0 ? -iy : (iy >= p.Hin ? 2 * p.Hin - 2 - iy : iy);
-            ix = ix < 0 ? -ix : (ix >= p.Win ? 2 * p.Win - 2 - ix : ix);
-          } else {
-            ok = ok && (static_cast<unsigned>(iy) < static_cast<unsigned>(p.Hin)) &&
-                 (static_cast<unsigned>(ix) < static_cast<unsigned>(p.Win));
-          }
-          if (up) { iy >>= 1; ix >>= 1; }
-          const size_t off = ok ? ((static_cast<size_t>(row_img[i]) * Hs + iy) * Ws + ix) * Cs + cc : 0;
-          cp_async_16(dst + i * 2048, sbase + off * 2, ok ? 16u : 0u);
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          const uint32_t code = second ? info[i].w : info[i].y;
+          const uint32_t base = second ? info[i].z : info[i].x;
+          const uint32_t dy = (code >> shy) & 15u, dx = (code >> shx) & 15u;
+          const bool ok = ((dy | dx | padmask) & 8u) == 0u;
+          const uint32_t off = ok ? base + dy * rstride + dx * pstride + cc : 0u;
+          cp_async_16_zfill(dst + i * 4096, sbase + static_cast<size_t>(off) * 2, ok);
         }
-        cp_async_commit();
-        if (it >= static_cast<uint32_t>(LAG)) {
-          cp_async_wait<LAG>();
-          fence_proxy_async_smem();
-          mbar_arrive(&full_bar[(it - LAG) % STAGES]);
-        }
+        // the stage is published to the MMA warp when every producer thread's copies have landed
+        cp_async_mbar_arrive_noinc(&full_bar[s]);
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (uint32_t j = (it >= static_cast<uint32_t>(LAG) ? it - LAG : 0u); j < it; ++j) mbar_arrive(&full_bar[j % STAGES]);
-  } else if (warp == 4) {
+  } else if (warp == MMA_WARP) {
     // =============================== MMA ISSUER ===============================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(BM, BN, p.fmt, p.fmt, 0, 0);
@@ -233,87 +271,91 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
     __syncwarp();
   } else {
     // =============================== EPILOGUE ===============================
-    const int q = warp & 3;            // TMEM lane quadrant this warp is allowed to read
+    // 8 warps: warp%4 selects the TMEM lane quadrant it may read, (warp-EPI_FIRST_WARP)/4 the column half.
+    const int q = warp & 3;
+    const int half = (warp - EPI_FIRST_WARP) >> 2;
     const int row = q * 32 + lane;
     const int e = tid - EPI_FIRST_WARP * 32;
+    constexpr int CW = 16;
+    constexpr int COLS_PER_HALF = (BN >= 32) ? BN / 2 : BN;
+    const int col_begin = (BN >= 32) ? half * COLS_PER_HALF : 0;
+    const bool active = (BN >= 32) || (half == 0);
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
       const uint32_t acc = ti & 1;
-      named_bar_sync(1, 128);          // everyone finished reading the previous tile's scale/shift
-      for (int j = e; j < BN; j += 128) {
+      named_bar_sync(1, NUM_EPI_THREADS);          // everyone finished reading the previous tile's scale/shift
+      for (int j = e; j < BN; j += NUM_EPI_THREADS) {
         const int n = n_tile * BN + j;
         s_scale[j] = (p.scale != nullptr && n < p.N) ? p.scale[n] : 1.f;
         s_shift[j] = (p.shift != nullptr && n < p.N) ? p.shift[n] : 0.f;
       }
-      named_bar_sync(1, 128);
-      mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1, 4);
+      named_bar_sync(1, NUM_EPI_THREADS);
+      mbar_wait<128>(&tmem_full_bar[acc], (ti >> 1) & 1, 4);
       tcgen05_fence_after();
       const int m = m_tile * BM + row;
       const bool m_ok = m < p.M;
-      constexpr int CW = (BN >= 32) ? 32 : 16;
+      if (active) {
 #pragma unroll 1
-      for (int j = 0; j < BN; j += CW) {
-        uint32_t v[CW];
-        const uint32_t taddr = tmem_base + acc * BN + j + (static_cast<uint32_t>(q * 32) << 16);
-        if constexpr (CW == 32) tmem_ld_32x32b_x32(taddr, v); else tmem_ld_32x32b_x16(taddr, v);
-        tmem_ld_wait();
-        const int n0 = n_tile * BN + j;
-        if (m_ok && n0 < p.N) {
-          float f[CW];
+        for (int j = col_begin; j < col_begin + COLS_PER_HALF; j += CW) {
+          uint32_t v[CW];
+          const uint32_t taddr = tmem_base + acc * BN + j + (static_cast<uint32_t>(q * 32) << 16);
+          tmem_ld_32x32b_x16(taddr, v);
+          tmem_ld_wait();
+          const int n0 = n_tile * BN + j;
+          if (m_ok && n0 < p.N) {
+            float f[CW];
 #pragma unroll
-          for (int x = 0; x < CW; ++x) f[x] = __uint_as_float(v[x]) * s_scale[j + x] + s_shift[j + x];
-          const int ncols = min(CW, p.N - n0);
-          if (p.residual != nullptr) {
-            const uint8_t* rp = p.residual + (static_cast<size_t>(m) * p.res_ld + n0) * 2;
-            if (ncols == CW) {
+            for (int x = 0; x < CW; ++x) f[x] = __uint_as_float(v[x]) * s_scale[j + x] + s_shift[j + x];
+            const int ncols = min(CW, p.N - n0);
+            if (p.residual != nullptr) {
+              const uint8_t* rp = p.residual + (static_cast<size_t>(m) * p.res_ld + n0) * 2;
+              if (ncols == CW) {
 #pragma unroll
-              for (int x = 0; x < CW / 8; ++x) {
-                const uint4 r = *reinterpret_cast<const uint4*>(rp + x * 16);
-                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                  const float2 t = unpack2(rr[y], p.fmt);
-                  f[x * 8 + 2 * y] += t.x;
-                  f[x * 8 + 2 * y + 1] += t.y;
+                for (int x = 0; x < CW / 8; ++x) {
+                  const uint4 r = *reinterpret_cast<const uint4*>(rp + x * 16);
+                  float2 t;
+                  t = unpack2(r.x, p.fmt); f[x * 8 + 0] += t.x; f[x * 8 + 1] += t.y;
+                  t = unpack2(r.y, p.fmt); f[x * 8 + 2] += t.x; f[x * 8 + 3] += t.y;
+                  t = unpack2(r.z, p.fmt); f[x * 8 + 4] += t.x; f[x * 8 + 5] += t.y;
+                  t = unpack2(r.w, p.fmt); f[x * 8 + 6] += t.x; f[x * 8 + 7] += t.y;
                 }
-              }
-            } else {
-              for (int x = 0; x < ncols; ++x) {
-                const uint16_t h = *reinterpret_cast<const uint16_t*>(rp + x * 2);
-                f[x] += unpack2(h, p.fmt).x;
+              } else {
+#pragma unroll
+                for (int x = 0; x < CW; ++x)
+                  if (x < ncols) f[x] += unpack2(*reinterpret_cast<const uint16_t*>(rp + x * 2), p.fmt).x;
               }
             }
-          }
 #pragma unroll
-          for (int x = 0; x < CW; ++x) f[x] = apply_act(f[x], p.act);
-          if (p.out_f32) {
-            float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + n0;
-            if (ncols == CW && (p.out_ld & 3) == 0) {
+            for (int x = 0; x < CW; ++x) f[x] = apply_act(f[x], p.act);
+            if (p.out_f32) {
+              float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + n0;
+              if (ncols == CW && (p.out_ld & 3) == 0) {
 #pragma unroll
-              for (int x = 0; x < CW / 4; ++x)
-                *reinterpret_cast<float4*>(op + 4 * x) = make_float4(f[4 * x], f[4 * x + 1], f[4 * x + 2], f[4 * x + 3]);
-            } else {
+                for (int x = 0; x < CW / 4; ++x)
+                  *reinterpret_cast<float4*>(op + 4 * x) = make_float4(f[4 * x], f[4 * x + 1], f[4 * x + 2], f[4 * x + 3]);
+              } else {
 #pragma unroll
-              for (int x = 0; x < CW; ++x) if (x < ncols) op[x] = f[x];
-            }
-          } else {
-            uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (static_cast<size_t>(m) * p.out_ld + n0) * 2;
-            if (ncols == CW && (p.out_ld & 7) == 0) {
-#pragma unroll
-              for (int x = 0; x < CW / 8; ++x) {
-                uint4 o;
-                o.x = pack2(f[8 * x], f[8 * x + 1], p.fmt);
-                o.y = pack2(f[8 * x + 2], f[8 * x + 3], p.fmt);
-                o.z = pack2(f[8 * x + 4], f[8 * x + 5], p.fmt);
-                o.w = pack2(f[8 * x + 6], f[8 * x + 7], p.fmt);
-                *reinterpret_cast<uint4*>(op + 16 * x) = o;
+                for (int x = 0; x < CW; ++x) if (x < ncols) op[x] = f[x];
               }
             } else {
+              uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (static_cast<size_t>(m) * p.out_ld + n0) * 2;
+              if (ncols == CW && (p.out_ld & 7) == 0) {
 #pragma unroll
-              for (int x = 0; x < CW; ++x)
-                if (x < ncols) *reinterpret_cast<uint16_t*>(op + 2 * x) = static_cast<uint16_t>(pack2(f[x], 0.f, p.fmt) & 0xFFFF);
+                for (int x = 0; x < CW / 8; ++x) {
+                  uint4 o;
+                  o.x = pack2(f[8 * x], f[8 * x + 1], p.fmt);
+                  o.y = pack2(f[8 * x + 2], f[8 * x + 3], p.fmt);
+                  o.z = pack2(f[8 * x + 4], f[8 * x + 5], p.fmt);
+                  o.w = pack2(f[8 * x + 6], f[8 * x + 7], p.fmt);
+                  *reinterpret_cast<uint4*>(op + 16 * x) = o;
+                }
+              } else {
+#pragma unroll
+                for (int x = 0; x < CW; ++x)
+                  if (x < ncols) *reinterpret_cast<uint16_t*>(op + 2 * x) = static_cast<uint16_t>(pack2(f[x], 0.f, p.fmt) & 0xFFFF);
+              }
             }
           }
         }
@@ -326,7 +368,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -371,14 +413,16 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
   if (cl2 < 3) return set_error(FP_ERR_ARG, "fp_conv_fwd: c0+c1=%d must be a power of two >= 8", cin);
   if ((d->c0 & 7) || (d->c1 & 7)) return set_error(FP_ERR_ARG, "fp_conv_fwd: channel counts must be multiples of 8");
   if (d->c1 > 0 && src1 == nullptr) return set_error(FP_ERR_ARG, "fp_conv_fwd: src1 is null but c1=%d", d->c1);
-  if (d->kpad % 64 || d->kpad < d->kh * d->kw * cin) return set_error(FP_ERR_ARG, "fp_conv_fwd: bad kpad %d", d->kpad);
+  if (d->kpad % 64 || d->kpad < d->kh * d->kw * cin || d->kpad > 8 * KTAB_ENTRIES) return set_error(FP_ERR_ARG, "fp_conv_fwd: bad kpad %d", d->kpad);
   if (d->npad % d->bn || d->npad < d->cout) return set_error(FP_ERR_ARG, "fp_conv_fwd: bad npad %d (bn %d, cout %d)", d->npad, d->bn, d->cout);
   if (d->dtype != FP_F16 && d->dtype != FP_BF16) return set_error(FP_ERR_ARG, "fp_conv_fwd: bad dtype");
   const int Hin = d->up0 ? 2 * d->h0 : d->h0, Win = d->up0 ? 2 * d->w0 : d->w0;
   if (d->pad_mode == FP_PAD_REFLECT && (d->pad_t > 1 || d->pad_l > 1 || Hin < 2 || Win < 2 || d->kh > 3 || d->kw > 3))
     return set_error(FP_ERR_UNSUPPORTED, "fp_conv_fwd: reflection padding is implemented for pad 1, 3x3 only");
-  if (Hin * d->stride + 64 >= 65536 || Win * d->stride + 64 >= 65536 || d->batch <= 0)
-    return set_error(FP_ERR_UNSUPPORTED, "fp_conv_fwd: spatial size too large");
+  if (d->kh > 4 || d->kw > 4 || d->kh < 1 || d->kw < 1) return set_error(FP_ERR_UNSUPPORTED, "fp_conv_fwd: kernel size must be 1..4");
+  if (d->batch <= 0 || static_cast<long long>(d->batch) * d->h0 * d->w0 * d->c0 >= (1ll << 31) ||
+      static_cast<long long>(d->batch) * Hin * Win * d->c1 >= (1ll << 31))
+    return set_error(FP_ERR_UNSUPPORTED, "fp_conv_fwd: a source tensor has >= 2^31 elements; split the batch");
   int rc = fp_check_device();
   if (rc != FP_OK) return rc;
 
@@ -391,7 +435,7 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
   p.out = out;
   p.C0 = d->c0; p.C1 = d->c1; p.H0 = d->h0; p.W0 = d->w0; p.up0 = d->up0;
   p.Hin = Hin; p.Win = Win;
-  p.cin_log2 = cl2; p.taps = d->kh * d->kw; p.KW = d->kw; p.stride = d->stride;
+  p.cin_log2 = cl2; p.taps = d->kh * d->kw; p.KH = d->kh; p.KW = d->kw; p.stride = d->stride;
   p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.pad_mode = d->pad_mode;
   p.Ho = d->ho; p.Wo = d->wo; p.HoWo = d->ho * d->wo; p.M = d->batch * d->ho * d->wo; p.N = d->cout;
   p.num_kb = d->kpad / 64; p.kpad = d->kpad;

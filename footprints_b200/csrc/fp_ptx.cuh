@@ -45,14 +45,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef FP_SPIN_TIMEOUT_CYCLES
 #define FP_SPIN_TIMEOUT_CYCLES (4000000000ll)  // ~2 s at 2 GHz: a protocol bug traps instead of hanging the box
 #endif
+// SLEEP_NS > 0: back off between polls (for waiters that are not latency critical, so that their spin
+// does not steal issue slots from the producer warps sharing the scheduler).
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t polls = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > FP_SPIN_TIMEOUT_CYCLES) {
-      printf("[footprints_b200] mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x,
-             threadIdx.x, parity);
-      __trap();
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    if ((++polls & 0x3FFu) == 0u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > FP_SPIN_TIMEOUT_CYCLES) {
+        printf("[footprints_b200] mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x,
+               threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }
@@ -65,6 +73,21 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, 
                : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// 16-byte copy, or 16 bytes of zeros when `valid` is false (the ignore-src form: no size arithmetic)
+__device__ __forceinline__ void cp_async_16_zfill(uint32_t dst_smem, const void* src, bool valid) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, %2, 0;\n\t"
+      "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t}"
+      ::"r"(dst_smem), "l"(src), "r"(static_cast<uint32_t>(valid))
+      : "memory");
+}
+// Asynchronous arrive: the mbarrier receives one arrival when all cp.async issued so far by this thread have
+// landed in shared memory (.noinc: the arrival is part of the barrier's expected count).  The issuing
+// thread never blocks, so every pipeline stage can be in flight at once.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");

@@ -1,0 +1,78 @@
+"""CPU-only checks of the host side: state_dict/contract parity with the reference layout, the C ABI
+exports every symbol the header declares, and the no-fallback behaviour."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from footprints_b200 import FootprintNetwork, FootprintsModel, ModelManager, _lib
+from footprints_b200.synthetic import state_spec, synthetic_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('arch,blocks', [('resnet34', (3, 4, 6, 3)), ('resnet18', (2, 2, 2, 2))])
+def test_state_dict_matches_reference_layout(arch, blocks):
+    net = FootprintNetwork(pretrained=False, blocks=blocks)
+    sd = net.state_dict()
+    spec = state_spec(arch)
+    assert list(sd.keys()) == list(spec.keys())
+    for k, shape in spec.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    if arch == 'resnet34':
+        assert len(sd) == 484
+        n_grad = sum(p.numel() for p in net.parameters())
+        assert n_grad == 31021392
+    # a reference-format checkpoint loads strictly
+    net.load_state_dict(synthetic_state_dict(arch, 0), strict=True)
+    assert FootprintsModel is FootprintNetwork
+
+
+def test_random_init_matches_reference_constructor():
+    """Same seed -> same random-init weights as the reference constructor (needs /root/reference)."""
+    if not os.path.isdir('/root/reference/footprints'):
+        pytest.skip('reference checkout not present on this machine')
+    import torchvision
+    sys.path.insert(0, '/root/reference')
+    import footprints.network as fn
+    fn.resnet34 = lambda pretrained=True: torchvision.models.resnet34(weights=None)
+    torch.manual_seed(0)
+    ref = fn.FootprintNetwork(pretrained=False).state_dict()
+    torch.manual_seed(0)
+    ours = FootprintNetwork(pretrained=False).state_dict()
+    assert list(ref.keys()) == list(ours.keys())
+    for k in ref:
+        assert torch.equal(ref[k], ours[k]), k
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'footprints_b200.h')).read()
+    declared = set(re.findall(r'\b(fp_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in the header but not exported'
+    assert declared == set(_lib.PROTOTYPES.keys()), (declared ^ set(_lib.PROTOTYPES.keys()))
+    _lib.load()
+    assert lib.fp_version() == 100
+
+
+def test_no_cpu_fallback():
+    net = FootprintNetwork(pretrained=False).eval()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        net(torch.rand(1, 3, 64, 96))
+
+
+def test_model_manager_surface(tmp_path):
+    mm = ModelManager(save_folder=str(tmp_path), use_cuda=False, is_inference=False, pretrained=False)
+    assert isinstance(mm.optimiser, torch.optim.Adam)
+    assert isinstance(mm.scheduler, torch.optim.lr_scheduler.StepLR)
+    mm.save_model('weights_0')
+    assert os.path.exists(tmp_path / 'weights_0' / 'model.pth')
+    mm2 = ModelManager(save_folder=str(tmp_path), use_cuda=False, is_inference=True, pretrained=False)
+    mm2.load_model(str(tmp_path / 'weights_0'))
+    for a, b in zip(mm.model.state_dict().values(), mm2.model.state_dict().values()):
+        assert torch.equal(a, b)
