@@ -14,6 +14,8 @@ FP_ACT_NONE, FP_ACT_RELU, FP_ACT_ELU, FP_ACT_SIGMOID = 0, 1, 2, 3
 FP_PAD_ZERO, FP_PAD_REFLECT = 0, 1
 
 _i32 = ctypes.c_int32
+_i64 = ctypes.c_longlong
+_f32 = ctypes.c_float
 _vp = ctypes.c_void_p
 
 
@@ -21,7 +23,7 @@ class FpConvDesc(ctypes.Structure):
     _fields_ = [(n, _i32) for n in (
         'batch', 'c0', 'h0', 'w0', 'up0', 'c1', 'kh', 'kw', 'stride', 'pad_t', 'pad_l', 'pad_mode',
         'ho', 'wo', 'cout', 'kpad', 'npad', 'bn', 'act', 'dtype', 'out_f32', 'out_ld', 'res_ld',
-        'b_via_tma')]
+        'b_via_tma', 'w_dtype_plus1')]
 
 
 # name -> (restype, argtypes); every name must be exported by the library (tests check this against
@@ -31,11 +33,25 @@ PROTOTYPES = {
     'fp_last_error': (ctypes.c_char_p, []),
     'fp_check_device': (ctypes.c_int, []),
     'fp_conv_fwd': (ctypes.c_int, [ctypes.POINTER(FpConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'fp_pack_conv_weight': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    'fp_pack_conv_weight': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_pack_stem_weight': (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     'fp_stem_prep': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_maxpool3x3s2': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_heads_to_nchw': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    'fp_reduce_workspace_floats': (ctypes.c_int, [_i32]),
+    'fp_bn_stats': (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'fp_bn_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
+    'fp_bn_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'fp_bias_grad': (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    'fp_loss_fwd_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp, _vp]),
+    'fp_heads_bwd': (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    'fp_fold_bwd': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp]),
+    'fp_act_bwd': (ctypes.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
+    'fp_grad_add': (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    'fp_maxpool3x3s2_bwd': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    'fp_conv_wgrad_workspace_bytes': (ctypes.c_longlong, [ctypes.POINTER(FpConvDesc)]),
+    'fp_conv_wgrad': (ctypes.c_int, [ctypes.POINTER(FpConvDesc), _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    'fp_adam_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
 }
 
 _lib = None

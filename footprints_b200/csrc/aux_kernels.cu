@@ -17,18 +17,18 @@ __device__ __forceinline__ uint16_t to16(float v, int fmt) {
 }
 
 // ---------------------------------------------------------------------------------- weight packing
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int kh, int kw, int npad,
-                                        int kpad, int fmt, int flip, uint16_t* __restrict__ out) {
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int kh, int kw, int cpad,
+                                        int npad, int kpad, int fmt, int flip, uint16_t* __restrict__ out) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(npad) * kpad) return;
   const int n = static_cast<int>(idx / kpad);
   const int k = static_cast<int>(idx - static_cast<long long>(n) * kpad);
-  const int inner = flip ? cout : cin;   // channel-minor extent of K
+  const int inner = flip ? cout : cin;   // channel-minor extent of K (padded to cpad in the packed layout)
   const int rows = flip ? cin : cout;
-  const int tap = k / inner;
-  const int c = k - tap * inner;
+  const int tap = k / cpad;
+  const int c = k - tap * cpad;
   float v = 0.f;
-  if (n < rows && tap < kh * kw) {
+  if (n < rows && tap < kh * kw && c < inner) {
     const int ky = tap / kw, kx = tap - ky * kw;
     if (!flip) v = w[((static_cast<long long>(n) * cin + c) * kh + ky) * kw + kx];
     else v = w[((static_cast<long long>(c) * cin + n) * kh + (kh - 1 - ky)) * kw + (kw - 1 - kx)];
@@ -160,14 +160,15 @@ static inline unsigned blocks_for(long long n, int threads) { return static_cast
 
 using namespace fp;
 
-extern "C" int fp_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int npad, int kpad, int dtype,
-                                   int flip, void* out, void* stream) {
+extern "C" int fp_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int cpad, int npad, int kpad,
+                                   int dtype, int flip, void* out, void* stream) {
   if (!w || !out) return set_error(FP_ERR_ARG, "fp_pack_conv_weight: null argument");
   const int rows = flip ? cin : cout, inner = flip ? cout : cin;
-  if (npad < rows || kpad < kh * kw * inner) return set_error(FP_ERR_ARG, "fp_pack_conv_weight: npad/kpad too small");
+  if (cpad < inner || npad < rows || kpad < kh * kw * cpad)
+    return set_error(FP_ERR_ARG, "fp_pack_conv_weight: cpad/npad/kpad too small");
   const long long n = static_cast<long long>(npad) * kpad;
   pack_conv_weight_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, cout, cin, kh, kw, npad, kpad, dtype, flip, static_cast<uint16_t*>(out));
+      w, cout, cin, kh, kw, cpad, npad, kpad, dtype, flip, static_cast<uint16_t*>(out));
   FP_CHECK_LAUNCH("fp_pack_conv_weight");
   return FP_OK;
 }

@@ -15,7 +15,9 @@
 //                          mainloop overlaps), apply scale/shift (+residual) + activation, store NHWC.
 #include "fp_ptx.cuh"
 #include "fp_internal.h"
+#include "igemm_common.cuh"
 
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -44,20 +46,18 @@ struct IgemmCfg {
 };
 
 struct IgemmParams {
-  const uint8_t* src0;
-  const uint8_t* src1;
+  GatherGeom g;
   const uint8_t* w_packed;   // only used when !b_via_tma
   const float* scale;
   const float* shift;
   const uint8_t* residual;
   void* out;
-  int C0, C1, H0, W0, up0;
-  int Hin, Win;              // virtual input size (after upsample) == source 1 size
-  int cin_log2, taps, KH, KW, stride, pad_t, pad_l, pad_mode;
-  int Ho, Wo, HoWo, M, N;
+  int N;
   int num_kb, kpad, m_tiles, n_tiles, total_tiles;
-  int act, fmt, out_f32, out_ld, res_ld, b_via_tma;
+  int act, fmt, w_fmt, out_f32, out_ld, res_ld, b_via_tma;
+  int debug;                 // FP_DEBUG_FLAGS (perf triage only): 1 skip A gather, 2 skip MMA, 4 skip epilogue math, 8 skip B load
 };
+
 
 // ELU(alpha=1) negative branch: expm1 via a short Taylor series near 0 and ex2.approx elsewhere
 // (abs error < 1e-7, far below the 16-bit output rounding).
@@ -83,34 +83,6 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
 __device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
   if (fmt == FP_BF16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
   return __half22float2(*reinterpret_cast<__half2*>(&u));
-}
-
-// Per output row and per source: element offset of the reference source pixel (the first in-range tap)
-// plus 4-bit per-tap row/column deltas relative to it (15 = tap reads padding zeros).  Encodes zero and
-// reflection padding, stride, and the nearest x2 upsample; the K loop then needs ~10 instructions per
-// 16-byte cp.async instead of re-deriving the mapping.
-__device__ __forceinline__ void make_row_info(int n, int y0, int x0, int Hv, int Wv, int up, int Hs, int Ws, int Cs,
-                                              int KH, int KW, int reflect, uint32_t& base, uint32_t& code) {
-  const int refy = max(y0, 0) >> up, refx = max(x0, 0) >> up;
-  base = static_cast<uint32_t>(((n * Hs + refy) * Ws + refx) * Cs);
-  uint32_t cd = 0;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    int vy = y0 + t, vx = x0 + t;
-    bool oky = t < KH, okx = t < KW;
-    if (reflect) {
-      vy = vy < 0 ? -vy : (vy >= Hv ? 2 * Hv - 2 - vy : vy);
-      vx = vx < 0 ? -vx : (vx >= Wv ? 2 * Wv - 2 - vx : vx);
-    } else {
-      oky = oky && static_cast<unsigned>(vy) < static_cast<unsigned>(Hv);
-      okx = okx && static_cast<unsigned>(vx) < static_cast<unsigned>(Wv);
-    }
-    const uint32_t dy = oky ? static_cast<uint32_t>((vy >> up) - refy) : 15u;
-    const uint32_t dx = okx ? static_cast<uint32_t>((vx >> up) - refx) : 15u;
-    cd |= (dy & 15u) << (4 * t);
-    cd |= (dx & 15u) << (16 + 4 * t);
-  }
-  code = cd;
 }
 
 template <int BN>
@@ -152,20 +124,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
     if (p.b_via_tma) tma_prefetch_desc(&tmap_w);
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-  // K-chunk table: chunk j covers channels [8j, 8j+8) of the tap-major K axis.  Entry bits:
-  //   [0,5) row-code shift (4*th)   [5,10) col-code shift (16+4*tw)   bit 10 source 1   bit 11 chunk is K padding
-  //   [12,32) channel offset inside the source pixel
-  for (int j = tid; j < p.num_kb * 8; j += NUM_THREADS) {
-    const int ch0 = j * 8;
-    const int tap = ch0 >> p.cin_log2;
-    int cc = ch0 & ((p.C0 + p.C1) - 1);
-    const int th = tap / p.KW, tw = tap - th * p.KW;
-    const uint32_t second = cc >= p.C0 ? 1u : 0u;
-    if (second) cc -= p.C0;
-    const uint32_t pad = tap >= p.taps ? 1u : 0u;
-    s_ktab[j] = pad ? (1u << 11) : (static_cast<uint32_t>(4 * th) | (static_cast<uint32_t>(16 + 4 * tw) << 5) | (second << 10) |
-                                     (static_cast<uint32_t>(cc) << 12));
-  }
+  for (int j = tid; j < p.num_kb * 8; j += NUM_THREADS) s_ktab[j] = make_ktab_entry(p.g, j, p.num_kb * 8);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -186,15 +145,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
       if (tid < BM) {
         const int m = m_tile * BM + tid;
         uint4 ri = make_uint4(0u, 0xFFFFFFFFu, 0u, 0xFFFFFFFFu);
-        if (m < p.M) {
-          const int n = m / p.HoWo;
-          const int rem = m - n * p.HoWo;
-          const int oy = rem / p.Wo;
-          const int ox = rem - oy * p.Wo;
-          const int y0 = oy * p.stride - p.pad_t, x0 = ox * p.stride - p.pad_l;
-          make_row_info(n, y0, x0, p.Hin, p.Win, p.up0, p.H0, p.W0, p.C0, p.KH, p.KW, p.pad_mode, ri.x, ri.y);
-          if (p.C1 > 0) make_row_info(n, y0, x0, p.Hin, p.Win, 0, p.Hin, p.Win, p.C1, p.KH, p.KW, p.pad_mode, ri.z, ri.w);
-        }
+        if (m < p.g.M) ri = make_row_info_for_pixel(p.g, m);
         info_buf[tid] = ri;
       }
       named_bar_sync(2, NUM_PRODUCER_THREADS);
@@ -209,8 +160,11 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
         __syncwarp();
         if (p.b_via_tma) {
           if (tid == 0) {
-            mbar_arrive_expect_tx(&full_bar[s], B_STAGE_BYTES);
-            tma_load_2d(smem_u32(b_smem) + s * B_STAGE_BYTES, &tmap_w, &full_bar[s], kb * BK, n_tile * BN);
+            if (p.debug & 8) mbar_arrive(&full_bar[s]);
+            else {
+              mbar_arrive_expect_tx(&full_bar[s], B_STAGE_BYTES);
+              tma_load_2d(smem_u32(b_smem) + s * B_STAGE_BYTES, &tmap_w, &full_bar[s], kb * BK, n_tile * BN);
+            }
           }
         } else {
           const uint8_t* wsrc = p.w_packed + (static_cast<size_t>(n_tile) * BN * p.kpad + kb * BK + c * 8) * 2;
@@ -221,22 +175,15 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
           }
         }
         // decode this thread's K chunk (tap, channel slice, source) from the table built at kernel start
-        const uint32_t ke = s_ktab[kb * 8 + c];
-        const bool second = (ke & (1u << 10)) != 0u;
-        const uint32_t padmask = (ke >> 8) & 8u;                             // bit 11 -> 8: forces "invalid"
-        const uint32_t shy = ke & 31u, shx = (ke >> 5) & 31u, cc = ke >> 12;
-        const uint8_t* sbase = second ? p.src1 : p.src0;
-        const uint32_t pstride = second ? p.C1 : p.C0;                       // elements per source pixel
-        const uint32_t rstride = second ? p.Win * p.C1 : p.W0 * p.C0;        // elements per source row
+        const KDecode kd = decode_ktab(p.g, s_ktab[kb * 8 + c]);
         const uint32_t dst = a_dst0 + s * A_STAGE_BYTES;
+        if (!(p.debug & 1)) {
 #pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          const uint32_t code = second ? info[i].w : info[i].y;
-          const uint32_t base = second ? info[i].z : info[i].x;
-          const uint32_t dy = (code >> shy) & 15u, dx = (code >> shx) & 15u;
-          const bool ok = ((dy | dx | padmask) & 8u) == 0u;
-          const uint32_t off = ok ? base + dy * rstride + dx * pstride + cc : 0u;
-          cp_async_16_zfill(dst + i * 4096, sbase + static_cast<size_t>(off) * 2, ok);
+          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+            bool ok;
+            const uint32_t off = gather_offset(kd, info[i], ok);
+            cp_async_16_zfill(dst + i * 4096, kd.sbase + static_cast<size_t>(off) * 2, ok);
+          }
         }
         // the stage is published to the MMA warp when every producer thread's copies have landed
         cp_async_mbar_arrive_noinc(&full_bar[s]);
@@ -245,7 +192,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
   } else if (warp == MMA_WARP) {
     // =============================== MMA ISSUER ===============================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(BM, BN, p.fmt, p.fmt, 0, 0);
+      const uint32_t idesc = umma_idesc_f16(BM, BN, p.fmt, p.w_fmt, 0, 0);
       uint32_t it = 0, ti = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
         const uint32_t acc = ti & 1;
@@ -260,6 +207,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
           const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(b_smem) + s * B_STAGE_BYTES, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
+            if (p.debug & 2) break;
             // advancing 16 K-elements = 32 bytes inside the swizzle row = +2 in the (addr >> 4) field
             umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
@@ -295,7 +243,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
       mbar_wait<128>(&tmem_full_bar[acc], (ti >> 1) & 1, 4);
       tcgen05_fence_after();
       const int m = m_tile * BM + row;
-      const bool m_ok = m < p.M;
+      const bool m_ok = m < p.g.M;
       if (active) {
 #pragma unroll 1
         for (int j = col_begin; j < col_begin + COLS_PER_HALF; j += CW) {
@@ -304,7 +252,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
           tmem_ld_32x32b_x16(taddr, v);
           tmem_ld_wait();
           const int n0 = n_tile * BN + j;
-          if (m_ok && n0 < p.N) {
+          if (m_ok && n0 < p.N && !(p.debug & 4)) {
             float f[CW];
 #pragma unroll
             for (int x = 0; x < CW; ++x) f[x] = __uint_as_float(v[x]) * s_scale[j + x] + s_shift[j + x];
@@ -404,44 +352,57 @@ static int ilog2_exact(int v) {
 
 using namespace fp;
 
+int fp::fill_gather_geom(const FpConvDesc* d, const void* src0, const void* src1, const char* who, GatherGeom& g) {
+  const int cin = d->c0 + d->c1;
+  const int cl2 = ilog2_exact(cin);
+  if (cl2 < 3) return set_error(FP_ERR_ARG, "%s: c0+c1=%d must be a power of two >= 8", who, cin);
+  if ((d->c0 & 7) || (d->c1 & 7)) return set_error(FP_ERR_ARG, "%s: channel counts must be multiples of 8", who);
+  if (d->c1 > 0 && src1 == nullptr) return set_error(FP_ERR_ARG, "%s: src1 is null but c1=%d", who, d->c1);
+  if (d->kpad % 64 || d->kpad < d->kh * d->kw * cin) return set_error(FP_ERR_ARG, "%s: bad kpad %d", who, d->kpad);
+  if (d->dtype != FP_F16 && d->dtype != FP_BF16) return set_error(FP_ERR_ARG, "%s: bad dtype", who);
+  if (d->up0 < 0 || d->up0 > 2 || (d->up0 == 2 && (d->c1 > 0 || d->pad_mode != FP_PAD_ZERO || d->stride != 1)))
+    return set_error(FP_ERR_ARG, "%s: bad up0 mode", who);
+  const int Hin = d->up0 ? 2 * d->h0 : d->h0, Win = d->up0 ? 2 * d->w0 : d->w0;
+  if (d->pad_mode == FP_PAD_REFLECT && (d->pad_t > 1 || d->pad_l > 1 || Hin < 2 || Win < 2 || d->kh > 3 || d->kw > 3))
+    return set_error(FP_ERR_UNSUPPORTED, "%s: reflection padding is implemented for pad 1, 3x3 only", who);
+  if (d->kh > 4 || d->kw > 4 || d->kh < 1 || d->kw < 1) return set_error(FP_ERR_UNSUPPORTED, "%s: kernel size must be 1..4", who);
+  if (d->batch <= 0 || static_cast<long long>(d->batch) * d->h0 * d->w0 * d->c0 >= (1ll << 31) ||
+      static_cast<long long>(d->batch) * Hin * Win * d->c1 >= (1ll << 31) ||
+      static_cast<long long>(d->batch) * d->ho * d->wo >= (1ll << 31))
+    return set_error(FP_ERR_UNSUPPORTED, "%s: a tensor has >= 2^31 elements; split the batch", who);
+  g.src0 = static_cast<const uint8_t*>(src0);
+  g.src1 = static_cast<const uint8_t*>(src1);
+  g.C0 = d->c0; g.C1 = d->c1; g.H0 = d->h0; g.W0 = d->w0; g.up0 = d->up0;
+  g.Hin = Hin; g.Win = Win;
+  g.cin_log2 = cl2; g.taps = d->kh * d->kw; g.KH = d->kh; g.KW = d->kw; g.stride = d->stride;
+  g.pad_t = d->pad_t; g.pad_l = d->pad_l; g.pad_mode = d->pad_mode;
+  g.Ho = d->ho; g.Wo = d->wo; g.HoWo = d->ho * d->wo; g.M = d->batch * d->ho * d->wo;
+  return FP_OK;
+}
+
 extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* src1, const void* w_packed,
                            const float* scale, const float* shift, const void* residual, void* out, void* stream) {
   if (d == nullptr || src0 == nullptr || w_packed == nullptr || out == nullptr)
     return set_error(FP_ERR_ARG, "fp_conv_fwd: null argument");
-  const int cin = d->c0 + d->c1;
-  const int cl2 = ilog2_exact(cin);
-  if (cl2 < 3) return set_error(FP_ERR_ARG, "fp_conv_fwd: c0+c1=%d must be a power of two >= 8", cin);
-  if ((d->c0 & 7) || (d->c1 & 7)) return set_error(FP_ERR_ARG, "fp_conv_fwd: channel counts must be multiples of 8");
-  if (d->c1 > 0 && src1 == nullptr) return set_error(FP_ERR_ARG, "fp_conv_fwd: src1 is null but c1=%d", d->c1);
-  if (d->kpad % 64 || d->kpad < d->kh * d->kw * cin || d->kpad > 8 * KTAB_ENTRIES) return set_error(FP_ERR_ARG, "fp_conv_fwd: bad kpad %d", d->kpad);
+  IgemmParams p{};
+  int rc = fill_gather_geom(d, src0, src1, "fp_conv_fwd", p.g);
+  if (rc != FP_OK) return rc;
+  if (d->kpad > 8 * KTAB_ENTRIES) return set_error(FP_ERR_UNSUPPORTED, "fp_conv_fwd: kpad %d too large", d->kpad);
   if (d->npad % d->bn || d->npad < d->cout) return set_error(FP_ERR_ARG, "fp_conv_fwd: bad npad %d (bn %d, cout %d)", d->npad, d->bn, d->cout);
-  if (d->dtype != FP_F16 && d->dtype != FP_BF16) return set_error(FP_ERR_ARG, "fp_conv_fwd: bad dtype");
-  const int Hin = d->up0 ? 2 * d->h0 : d->h0, Win = d->up0 ? 2 * d->w0 : d->w0;
-  if (d->pad_mode == FP_PAD_REFLECT && (d->pad_t > 1 || d->pad_l > 1 || Hin < 2 || Win < 2 || d->kh > 3 || d->kw > 3))
-    return set_error(FP_ERR_UNSUPPORTED, "fp_conv_fwd: reflection padding is implemented for pad 1, 3x3 only");
-  if (d->kh > 4 || d->kw > 4 || d->kh < 1 || d->kw < 1) return set_error(FP_ERR_UNSUPPORTED, "fp_conv_fwd: kernel size must be 1..4");
-  if (d->batch <= 0 || static_cast<long long>(d->batch) * d->h0 * d->w0 * d->c0 >= (1ll << 31) ||
-      static_cast<long long>(d->batch) * Hin * Win * d->c1 >= (1ll << 31))
-    return set_error(FP_ERR_UNSUPPORTED, "fp_conv_fwd: a source tensor has >= 2^31 elements; split the batch");
-  int rc = fp_check_device();
+  rc = fp_check_device();
   if (rc != FP_OK) return rc;
 
-  IgemmParams p{};
-  p.src0 = static_cast<const uint8_t*>(src0);
-  p.src1 = static_cast<const uint8_t*>(src1);
   p.w_packed = static_cast<const uint8_t*>(w_packed);
   p.scale = scale; p.shift = shift;
   p.residual = static_cast<const uint8_t*>(residual);
   p.out = out;
-  p.C0 = d->c0; p.C1 = d->c1; p.H0 = d->h0; p.W0 = d->w0; p.up0 = d->up0;
-  p.Hin = Hin; p.Win = Win;
-  p.cin_log2 = cl2; p.taps = d->kh * d->kw; p.KH = d->kh; p.KW = d->kw; p.stride = d->stride;
-  p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.pad_mode = d->pad_mode;
-  p.Ho = d->ho; p.Wo = d->wo; p.HoWo = d->ho * d->wo; p.M = d->batch * d->ho * d->wo; p.N = d->cout;
+  p.N = d->cout;
   p.num_kb = d->kpad / 64; p.kpad = d->kpad;
-  p.m_tiles = (p.M + BM - 1) / BM; p.n_tiles = d->npad / d->bn; p.total_tiles = p.m_tiles * p.n_tiles;
-  p.act = d->act; p.fmt = d->dtype; p.out_f32 = d->out_f32; p.out_ld = d->out_ld; p.res_ld = d->res_ld;
+  p.m_tiles = (p.g.M + BM - 1) / BM; p.n_tiles = d->npad / d->bn; p.total_tiles = p.m_tiles * p.n_tiles;
+  p.act = d->act; p.fmt = d->dtype; p.w_fmt = d->w_dtype_plus1 ? d->w_dtype_plus1 - 1 : d->dtype;
+  p.out_f32 = d->out_f32; p.out_ld = d->out_ld; p.res_ld = d->res_ld;
   p.b_via_tma = d->b_via_tma;
+  { const char* e = getenv("FP_DEBUG_FLAGS"); p.debug = e ? atoi(e) : 0; }
 
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));

@@ -1,0 +1,260 @@
+// Weight-gradient convolution on tcgen05 tensor cores (sm_100a).
+//
+//   dW[co][k] = sum over output pixels m of dZ[m][co] * A[m][k],   k = tap*cin + c  (the packed-weight order)
+//
+// where A is the same on-the-fly im2col gather as the forward convolution (zero / reflection padding, stride,
+// nearest x2 upsample of source 0, channel concat with source 1).  As a GEMM the reduction runs over pixels, so
+// both operands are "MN-major": a shared-memory tile [128 pixels][64 channels] (128-byte rows, 128B swizzle) is
+// consumed by UMMA with the pixel index as K (8 x K16 steps per tile).  One CTA owns a 128(co) x 128(k) block of
+// dW for a contiguous range of pixel blocks (split-K); fp32 partials go to a workspace and a second kernel sums
+// the splits in a fixed order (deterministic) and scatters into the OIHW fp32 gradient.
+//
+//   warps 0-7  producers : cp.async gather of the dZ tile (2 x [128 px][64 co]) and the im2col tile
+//                          (2 x [128 px][64 k]) per stage; asynchronous mbarrier arrive (never blocks)
+//   warp  8    MMA issuer: 8 x tcgen05.mma (M128 x N128 x K16, both operands MN-major) per stage
+//   warps 9-12 epilogue  : once, at the end: TMEM -> fp32 partial block
+#include "fp_ptx.cuh"
+#include "fp_internal.h"
+#include "igemm_common.cuh"
+
+namespace fp {
+
+constexpr int WG_STAGES = 3;
+constexpr int WG_SUBTILE = 128 * 64 * 2;               // 16 KB: [128 pixels][64 channels] 16-bit
+constexpr int WG_STAGE_BYTES = 4 * WG_SUBTILE;         // dZ x2, im2col x2
+constexpr int WG_PRODUCER_WARPS = 8;
+constexpr int WG_PRODUCER_THREADS = WG_PRODUCER_WARPS * 32;
+constexpr int WG_MMA_WARP = WG_PRODUCER_WARPS;
+constexpr int WG_EPI_FIRST_WARP = WG_MMA_WARP + 1;
+constexpr int WG_THREADS = (WG_EPI_FIRST_WARP + 4) * 32;   // 416
+constexpr int WG_KTAB = 16;                            // 16-byte K chunks per CTA (128 columns)
+constexpr int WG_BAR_BYTES = 64;                      // 7 mbarriers, padded so that what follows stays 16-byte aligned
+constexpr int WG_SMEM_BYTES = 1024 + WG_STAGES * WG_STAGE_BYTES + WG_BAR_BYTES + 16 + 2 * 128 * 16 + WG_KTAB * 4;
+
+struct WgradParams {
+  GatherGeom g;              // forward-input gather geometry
+  const uint8_t* dz;         // [M][dz_ld] 16-bit
+  int dz_ld, Cout, kpad;
+  int k_chunks, co_tiles, splits, blocks_per_split, num_pix_blocks;
+  float* partial;            // [splits][co_tiles*128][kpad]
+  int a_fmt, b_fmt;          // dZ format, activation format
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + WG_STAGES * WG_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + WG_STAGES;
+  uint64_t* done_bar = empty_bar + WG_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(full_bar) + WG_BAR_BYTES);
+  uint4* s_rowinfo = reinterpret_cast<uint4*>(tmem_ptr_smem + 4);     // [2][128]
+  uint32_t* s_ktab = reinterpret_cast<uint32_t*>(s_rowinfo + 2 * 128);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int unit = blockIdx.x;
+  const int k_chunk = unit % p.k_chunks; unit /= p.k_chunks;
+  const int co_tile = unit % p.co_tiles;
+  const int split = unit / p.co_tiles;
+  const int pb_begin = split * p.blocks_per_split;
+  const int pb_end = min(p.num_pix_blocks, pb_begin + p.blocks_per_split);
+  const int nblk = pb_end - pb_begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(&full_bar[s], WG_PRODUCER_THREADS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == WG_MMA_WARP) tmem_alloc(tmem_ptr_smem, 128);
+  if (tid < WG_KTAB) s_ktab[tid] = make_ktab_entry(p.g, k_chunk * WG_KTAB + tid, p.kpad / 8);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < WG_PRODUCER_WARPS) {
+    const int c = tid & 7, r0 = tid >> 3;
+    const uint32_t swz = static_cast<uint32_t>(r0 * 128 + ((c ^ (r0 & 7)) << 4));
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    for (int i = 0; i < nblk; ++i) {
+      const int pb = pb_begin + i;
+      const int s = i % WG_STAGES;
+      uint4* info_buf = s_rowinfo + (i & 1) * 128;
+      if (tid < 128) {
+        const int m = pb * 128 + tid;
+        uint4 ri = make_uint4(0u, 0xFFFFFFFFu, 0u, 0xFFFFFFFFu);
+        if (m < p.g.M) ri = make_row_info_for_pixel(p.g, m);
+        info_buf[tid] = ri;
+      }
+      named_bar_sync(2, WG_PRODUCER_THREADS);
+      if (lane == 0) mbar_wait(&empty_bar[s], ((i / WG_STAGES) & 1) ^ 1, 11);
+      __syncwarp();
+      const uint32_t stage_base = tiles_u32 + s * WG_STAGE_BYTES + swz;
+      // dZ sub-tiles: columns co_tile*128 + j*64 + c*8
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = co_tile * 128 + j * 64 + c * 8;
+        const bool col_ok = col < p.dz_ld;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int m = pb * 128 + r0 + 32 * r;
+          const bool ok = col_ok && m < p.g.M;
+          const size_t off = ok ? static_cast<size_t>(m) * p.dz_ld + col : 0;
+          cp_async_16_zfill(stage_base + j * WG_SUBTILE + r * 4096, p.dz + off * 2, ok);
+        }
+      }
+      // im2col sub-tiles: K chunks k_chunk*16 + j*8 + c
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t ke = s_ktab[j * 8 + c];
+        const KDecode kd = decode_ktab(p.g, ke);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint4 ri = info_buf[r0 + 32 * r];
+          bool ok;
+          const uint32_t off = gather_offset(kd, ri, ok);
+          cp_async_16_zfill(stage_base + (2 + j) * WG_SUBTILE + r * 4096, kd.sbase + static_cast<size_t>(off) * 2, ok);
+        }
+      }
+      cp_async_mbar_arrive_noinc(&full_bar[s]);
+    }
+  } else if (warp == WG_MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(128, 128, p.a_fmt, p.b_fmt, 1, 1);
+      for (int i = 0; i < nblk; ++i) {
+        const int s = i % WG_STAGES;
+        mbar_wait(&full_bar[s], (i / WG_STAGES) & 1, 12);
+        tcgen05_fence_after();
+        const uint32_t a_base = smem_u32(tiles) + s * WG_STAGE_BYTES;
+        const uint32_t b_base = a_base + 2 * WG_SUBTILE;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          // MN-major SW128: 16 pixels (K) = 2 groups of 8 rows, SBO = 1024 B; 64-channel blocks LBO = 16 KB apart
+          const uint64_t a_desc = umma_smem_desc_sw128(a_base + ks * 2048, WG_SUBTILE, 1024);
+          const uint64_t b_desc = umma_smem_desc_sw128(b_base + ks * 2048, WG_SUBTILE, 1024);
+          umma_f16(tmem_base, a_desc, b_desc, idesc, (i | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else {
+    // epilogue: thread <-> accumulator row = output channel co_tile*128 + row
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait<256>(done_bar, 0, 13);
+    tcgen05_fence_after();
+    float* dst = p.partial + (static_cast<size_t>(split) * p.co_tiles * 128 + co_tile * 128 + row) * p.kpad + k_chunk * 128;
+    const int ncols = min(128, p.kpad - k_chunk * 128);
+#pragma unroll 1
+    for (int j = 0; j < 128; j += 16) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_base + j + (static_cast<uint32_t>(q * 32) << 16), v);
+      tmem_ld_wait();
+      if (j < ncols) {
+        if (nblk > 0) {
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            *reinterpret_cast<float4*>(dst + j + 4 * x) =
+                make_float4(__uint_as_float(v[4 * x]), __uint_as_float(v[4 * x + 1]), __uint_as_float(v[4 * x + 2]),
+                            __uint_as_float(v[4 * x + 3]));
+        } else {
+#pragma unroll
+          for (int x = 0; x < 4; ++x) *reinterpret_cast<float4*>(dst + j + 4 * x) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == WG_MMA_WARP) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// dW_oihw[co][ci][ky][kx] (+)= sum over splits of partial[split][co][(ky*kw+kx)*cin + ci]; stem = 1 inverts the
+// space-to-depth packing of fp_pack_stem_weight.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int co_rows, int kpad, int cout,
+                                    int cin, int kh, int kw, int stem, int accumulate, float* __restrict__ dw) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(cout) * cin * kh * kw;
+  if (idx >= total) return;
+  const int kx = static_cast<int>(idx % kw);
+  const int ky = static_cast<int>((idx / kw) % kh);
+  const int ci = static_cast<int>((idx / (kw * kh)) % cin);
+  const int co = static_cast<int>(idx / (static_cast<long long>(kw) * kh * cin));
+  int k;
+  if (stem) {
+    const int bh = (ky + 1) >> 1, dy = (ky + 1) & 1, bw = (kx + 1) >> 1, dx = (kx + 1) & 1;
+    k = (bh * 4 + bw) * 16 + (dy * 2 + dx) * 4 + ci;
+  } else {
+    k = (ky * kw + kx) * cin + ci;
+  }
+  double s = 0.0;
+  for (int sp = 0; sp < splits; ++sp) s += partial[(static_cast<size_t>(sp) * co_rows + co) * kpad + k];
+  dw[idx] = (accumulate ? dw[idx] : 0.f) + static_cast<float>(s);
+}
+
+static void wgrad_plan(const FpConvDesc* d, int& k_chunks, int& co_tiles, int& splits, int& blocks_per_split,
+                       int& num_pix_blocks) {
+  const long long M = static_cast<long long>(d->batch) * d->ho * d->wo;
+  num_pix_blocks = static_cast<int>((M + 127) / 128);
+  k_chunks = (d->kpad + 127) / 128;
+  co_tiles = (d->cout + 127) / 128;
+  const int base = k_chunks * co_tiles;
+  int want = (2 * num_sms() + base - 1) / base;
+  if (want < 1) want = 1;
+  if (want > num_pix_blocks) want = num_pix_blocks;
+  blocks_per_split = (num_pix_blocks + want - 1) / want;
+  splits = (num_pix_blocks + blocks_per_split - 1) / blocks_per_split;
+}
+
+}  // namespace fp
+
+using namespace fp;
+
+extern "C" long long fp_conv_wgrad_workspace_bytes(const FpConvDesc* d) {
+  if (d == nullptr) return -1;
+  int kc, ct, sp, bps, npb;
+  wgrad_plan(d, kc, ct, sp, bps, npb);
+  return static_cast<long long>(sp) * ct * 128 * d->kpad * 4;
+}
+
+extern "C" int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* src1, const void* dz, int dz_ld,
+                             int grad_dtype, int stem, int accumulate, float* dw_oihw, float* workspace, void* stream) {
+  if (!d || !src0 || !dz || !dw_oihw || !workspace) return set_error(FP_ERR_ARG, "fp_conv_wgrad: null argument");
+  WgradParams p{};
+  int rc = fill_gather_geom(d, src0, src1, "fp_conv_wgrad", p.g);
+  if (rc != FP_OK) return rc;
+  if (dz_ld < d->cout || (dz_ld & 7)) return set_error(FP_ERR_ARG, "fp_conv_wgrad: dz_ld=%d must be a multiple of 8 >= cout", dz_ld);
+  rc = fp_check_device();
+  if (rc != FP_OK) return rc;
+  p.dz = static_cast<const uint8_t*>(dz);
+  p.dz_ld = dz_ld; p.Cout = d->cout; p.kpad = d->kpad;
+  wgrad_plan(d, p.k_chunks, p.co_tiles, p.splits, p.blocks_per_split, p.num_pix_blocks);
+  p.partial = workspace;
+  p.a_fmt = grad_dtype; p.b_fmt = d->dtype;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = p.k_chunks * p.co_tiles * p.splits;
+  conv_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(p);
+  FP_CHECK_LAUNCH("fp_conv_wgrad");
+  const int cin = stem ? 3 : d->c0 + d->c1;
+  const int kh = stem ? 7 : d->kh, kw = stem ? 7 : d->kw;
+  const long long total = static_cast<long long>(d->cout) * cin * kh * kw;
+  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      workspace, p.splits, p.co_tiles * 128, d->kpad, d->cout, cin, kh, kw, stem, accumulate, dw_oihw);
+  FP_CHECK_LAUNCH("fp_conv_wgrad(reduce)");
+  return FP_OK;
+}

@@ -135,7 +135,7 @@ static int run_case(const Case& c, bool time_it) {
   CK(cudaMemcpy(dshift, hshift.data(), c.cout * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dout, 0xFF, (size_t)M * c.cout * 4));
 
-  FPCK(fp_pack_conv_weight(dw, c.cout, cin, c.k, c.k, d.npad, d.kpad, c.dtype, 0, dwp, nullptr));
+  FPCK(fp_pack_conv_weight(dw, c.cout, cin, c.k, c.k, cin, d.npad, d.kpad, c.dtype, 0, dwp, nullptr));
   const float* sc = c.use_scale ? dscale : nullptr;
   const void* rs = c.use_res ? dres : nullptr;
   FPCK(fp_conv_fwd(&d, ds0, n1 ? ds1 : nullptr, dwp, sc, dshift, rs, dout, nullptr));

@@ -148,7 +148,7 @@ class Engine:
                 _lib.check(self.lib.fp_pack_stem_weight(_ptr(w), L.cout, L.npad, self.fmt, _ptr(L.w_packed), stream))
             else:
                 cin = L.cin0 + L.cin1
-                _lib.check(self.lib.fp_pack_conv_weight(_ptr(w), L.cout, cin, L.k, L.k, L.npad, L.kpad, self.fmt, 0,
+                _lib.check(self.lib.fp_pack_conv_weight(_ptr(w), L.cout, cin, L.k, L.k, cin, L.npad, L.kpad, self.fmt, 0,
                                                         _ptr(L.w_packed), stream))
             if L.bn is not None:
                 # eval-mode BN: y = (x - mean) / sqrt(var + eps) * gamma + beta  (torch BatchNorm2d)

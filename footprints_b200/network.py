@@ -13,7 +13,7 @@ operator in ``forward``.  All arithmetic happens in the sm_100a kernels of
 import torch
 import torch.nn as nn
 
-from .engine import Engine
+from .engine import Engine, SCALES
 
 
 class _Placeholder(nn.Module):
@@ -169,17 +169,32 @@ class FootprintNetwork(nn.Module):
         self.mask_decoder = SkipDecoder(apply_sigmoid=False)
         self.depth_decoder = SkipDecoder(apply_sigmoid=True)
         self.compute_dtype = compute_dtype
+        self.train_dtype = 'bf16'      # activations in .train() mode; gradients are always bf16
         self._engine = None
+        self._train_engine = None
 
     def engine(self):
         if self._engine is None:
             self._engine = Engine(self, self.compute_dtype)
         return self._engine
 
+    def train_engine(self):
+        if self._train_engine is None:
+            from .train_engine import TrainEngine
+            self._train_engine = TrainEngine(self, self.train_dtype)
+        return self._train_engine
+
     def forward(self, input_image):
         if not input_image.is_cuda:
             raise RuntimeError('footprints_b200.FootprintNetwork runs on a B200 only (no CPU fallback); '
                                'move the module and the input to cuda')
+        if self.training:
+            # batch-statistics BatchNorm + hand-written backward behind one autograd node
+            from collections import OrderedDict
+            from .autograd import NetFunction
+            params = [p for p in self.parameters() if p.requires_grad]
+            outs = NetFunction.apply(self, input_image, *params)
+            return OrderedDict(zip(SCALES, outs))
         return self.engine().forward(input_image)
 
 

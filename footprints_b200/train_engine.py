@@ -1,0 +1,427 @@
+"""Training step of the Footprints hot path on one B200: train-mode forward (batch-statistics
+BatchNorm), and the hand-written backward that replaces autograd over footprints/network.py
+(reference: footprints/training/train.py:153-156,224-225).
+
+Every arithmetic step is a C-ABI call into ``libfootprints_b200.so``:
+
+  forward   conv (tcgen05 implicit GEMM) -> fp_bn_stats -> fp_bn_apply      (encoder)
+            conv + bias + ELU fused                                          (decoders, as in eval)
+  backward  fp_heads_bwd -> per conv: fp_conv_wgrad, fp_bias_grad,
+            fp_conv_fwd with the flipped weights as a zero-padded full correlation (data gradient of
+            the padded virtual input) -> fp_fold_bwd (adjoint of reflect-pad / nearest x2 / concat,
+            fused with ELU')                                                 (decoders)
+            fp_bn_bwd -> fp_conv_wgrad -> fp_conv_fwd(flipped weights [, zero-inserted x2 for the
+            stride-2 layers]) with the residual-branch gradient added in the epilogue  (encoder)
+
+Gradients between layers are bf16 (range), parameter gradients fp32.
+"""
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+from ._lib import FP_ACT_ELU, FP_ACT_NONE, FP_ACT_RELU, FP_BF16, FP_PAD_ZERO, FpConvDesc
+from .engine import SCALES, Engine, _bn_tile, _ptr
+
+_RAW = object()   # sentinel: run the conv with no scale/shift (NULL pointers)
+
+
+class TrainEngine(Engine):
+
+    def __init__(self, net, compute_dtype='bf16'):
+        super().__init__(net, compute_dtype)
+        self.gfmt = FP_BF16
+        self.gdtype = torch.bfloat16
+        self._bn_state = {}
+        self._saved = None
+        self._red_ws = None
+        self._wg_ws = None
+        self._loss_ws = None
+
+    # ------------------------------------------------------------------------------ helpers
+    def _dev(self):
+        return self.layers['stem'].weight.device
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _reduce_ws(self):
+        if self._red_ws is None:
+            n = self.lib.fp_reduce_workspace_floats(512)
+            self._red_ws = torch.empty(n, dtype=torch.float32, device=self._dev())
+        return self._red_ws
+
+    def _desc(self, L, src0, src1, ho, wo, dtype=None):
+        b, h0, w0, c0 = src0.shape
+        d = FpConvDesc()
+        d.batch, d.c0, d.h0, d.w0, d.up0 = b, c0, h0, w0, L.up0
+        d.c1 = src1.shape[3] if src1 is not None else 0
+        d.kh = d.kw = L.k
+        d.stride, d.pad_t, d.pad_l, d.pad_mode = L.stride, L.pad, L.pad, L.pad_mode
+        d.ho, d.wo = ho, wo
+        d.cout, d.kpad, d.npad, d.bn = L.cout, L.kpad, L.npad, L.bn_tile
+        d.act = L.act
+        d.dtype = self.fmt if dtype is None else dtype
+        d.b_via_tma = 1
+        return d
+
+    def refresh_weights(self, force=False):
+        """Training: weights change every step, so pack unconditionally (forward and flipped)."""
+        stream = self._stream()
+        dev = self._dev()
+        for L in self.layers.values():
+            w = L.weight.detach()
+            if L.w_packed is None:
+                L.w_packed = torch.empty((L.npad, L.kpad), dtype=self.tdtype, device=dev)
+            cin = L.cin0 + L.cin1
+            if L.stem:
+                _lib.check(self.lib.fp_pack_stem_weight(_ptr(w), L.cout, L.npad, self.fmt, _ptr(L.w_packed), stream))
+            else:
+                _lib.check(self.lib.fp_pack_conv_weight(_ptr(w), L.cout, cin, L.k, L.k, cin, L.npad, L.kpad, self.fmt, 0,
+                                                        _ptr(L.w_packed), stream))
+                # data-gradient operand: rows = cin, K = taps * cout_pad, filter rotated by 180 degrees
+                if getattr(L, 'w_flip', None) is None:
+                    L.cpad_out = max(8, L.cout)
+                    L.d_bn = _bn_tile(cin)
+                    L.d_npad = (cin + L.d_bn - 1) // L.d_bn * L.d_bn
+                    L.d_kpad = (L.k * L.k * L.cpad_out + 63) // 64 * 64
+                    L.w_flip = torch.empty((L.d_npad, L.d_kpad), dtype=self.gdtype, device=dev)
+                _lib.check(self.lib.fp_pack_conv_weight(_ptr(w), L.cout, cin, L.k, L.k, L.cpad_out, L.d_npad, L.d_kpad,
+                                                        self.gfmt, 1, _ptr(L.w_flip), stream))
+            L.scale = None
+            L.shift = L.bias.detach() if L.bias is not None else None
+        self._weight_key = None
+
+    # ------------------------------------------------------------------------------ forward
+    def _conv_bn(self, L, src, residual, relu, stream, saved):
+        """conv -> batch-stat BatchNorm (-> + residual) (-> ReLU); saves z and y for the backward."""
+        b, h, w, _ = src.shape
+        ho, wo = (h // L.stride, w // L.stride) if not L.stem else (h, w)
+        z = torch.empty((b, ho, wo, L.cout), dtype=self.tdtype, device=src.device)
+        self._conv(L, src, None, z, None, stream, scale=_RAW, shift=_RAW, act=FP_ACT_NONE)
+        st = self._bn_state.get(L.name)
+        if st is None:
+            st = {k: torch.empty(L.cout, dtype=torch.float32, device=src.device) for k in ('scale', 'shift', 'mean', 'invstd')}
+            self._bn_state[L.name] = st
+        bn = L.bn
+        M = b * ho * wo
+        _lib.check(self.lib.fp_bn_stats(_ptr(z), M, L.cout, self.fmt, _ptr(bn.weight.detach()), _ptr(bn.bias.detach()),
+                                        _ptr(bn.running_mean), _ptr(bn.running_var), float(bn.momentum), float(bn.eps),
+                                        _ptr(st['scale']), _ptr(st['shift']), _ptr(st['mean']), _ptr(st['invstd']),
+                                        _ptr(self._reduce_ws()), stream))
+        y = torch.empty_like(z)
+        _lib.check(self.lib.fp_bn_apply(_ptr(z), _ptr(st['scale']), _ptr(st['shift']), _ptr(residual), 1 if relu else 0, M,
+                                        L.cout, self.fmt, _ptr(y), stream))
+        bn.num_batches_tracked += 1
+        saved[L.name] = (src, z, y)
+        return y
+
+    def _conv(self, L, src0, src1, out, residual, stream, scale=None, shift=None, act=None):
+        if scale is _RAW:
+            # temporarily present NULL scale/shift
+            s0, s1 = L.scale, L.shift
+            L.scale, L.shift = None, None
+            try:
+                super()._conv(L, src0, src1, out, residual, stream, act=act)
+            finally:
+                L.scale, L.shift = s0, s1
+        else:
+            super()._conv(L, src0, src1, out, residual, stream, scale, shift, act)
+
+    def forward_train(self, image):
+        """Train-mode forward (footprints/network.py:21-30 with BatchNorm in training mode).  Returns the
+        dict of four fp32 NCHW outputs and keeps what the backward needs."""
+        _lib.require_device()
+        b, _, h, w = image.shape
+        if h % 32 or w % 32:
+            raise RuntimeError(f'input height and width must be multiples of 32, got {h}x{w}')
+        image = image.contiguous().float()
+        self.refresh_weights()
+        stream = self._stream()
+        lib = self.lib
+        dev = image.device
+        sv = {}
+
+        def new(shape, dtype=None):
+            return torch.empty(shape, dtype=dtype or self.tdtype, device=dev)
+
+        s2d = new((b, h // 2, w // 2, 16))
+        _lib.check(lib.fp_stem_prep(_ptr(image), b, h, w, self.fmt, _ptr(s2d), stream))
+        f0 = self._conv_bn(self.layers['stem'], s2d, None, True, stream, sv)
+        x = new((b, h // 4, w // 4, 64))
+        _lib.check(lib.fp_maxpool3x3s2(_ptr(f0), b, h // 2, w // 2, 64, self.fmt, _ptr(x), stream))
+        sv['pool'] = x
+        feats = [f0]
+        last_li = 0
+        for li, c1, ds, c2 in self.enc_blocks:
+            if li != last_li:
+                feats.append(x)
+                last_li = li
+            t1 = self._conv_bn(c1, x, None, True, stream, sv)
+            idt = x
+            if ds is not None:
+                idt = self._conv_bn(ds, x, None, False, stream, sv)
+            x = self._conv_bn(c2, t1, idt, True, stream, sv)
+        feats.append(x)
+        sv['feats'] = feats
+
+        heads = {}
+        for dname in ('mask', 'depth'):
+            d = self.dec[dname]
+            x = feats[4]
+            for bi in range(1, 5):
+                skip = feats[4 - bi]
+                hh, ww = x.shape[1], x.shape[2]
+                co = d[f'b{bi}.pre1'].cout
+                t = new((b, hh, ww, co))
+                self._conv(d[f'b{bi}.pre1'], x, None, t, None, stream)
+                sv[d[f'b{bi}.pre1'].name] = (x, None, t)
+                t2 = new((b, hh, ww, co))
+                self._conv(d[f'b{bi}.pre2'], t, None, t2, None, stream)
+                sv[d[f'b{bi}.pre2'].name] = (t, None, t2)
+                t3 = new((b, 2 * hh, 2 * ww, co))
+                self._conv(d[f'b{bi}.post1'], t2, skip, t3, None, stream)
+                sv[d[f'b{bi}.post1'].name] = (t2, skip, t3)
+                x = new((b, 2 * hh, 2 * ww, co))
+                self._conv(d[f'b{bi}.post2'], t3, None, x, None, stream)
+                sv[d[f'b{bi}.post2'].name] = (t3, None, x)
+                if bi >= 2:
+                    hd = new((b, 2 * hh, 2 * ww, 2), torch.float32)
+                    self._conv(d[f'head{bi - 1}'], x, None, hd, None, stream)
+                    sv[d[f'head{bi - 1}'].name] = (x, None, hd)
+                    heads[(dname, bi - 1)] = hd
+            hh, ww = x.shape[1], x.shape[2]
+            t = new((b, 2 * hh, 2 * ww, 32))
+            self._conv(d['o4.c1'], x, None, t, None, stream)
+            sv[d['o4.c1'].name] = (x, None, t)
+            t2 = new((b, 2 * hh, 2 * ww, 32))
+            self._conv(d['o4.c2'], t, None, t2, None, stream)
+            sv[d['o4.c2'].name] = (t, None, t2)
+            hd = new((b, 2 * hh, 2 * ww, 2), torch.float32)
+            self._conv(d['head4'], t2, None, hd, None, stream)
+            sv[d['head4'].name] = (t2, None, hd)
+            heads[(dname, 4)] = hd
+
+        outputs = OrderedDict()
+        for hi, key in enumerate(SCALES, start=1):
+            scale = (8, 4, 2, 1)[hi - 1]
+            out = torch.empty((b, 4, h, w), dtype=torch.float32, device=dev)
+            mh = heads[('mask', hi)]
+            _lib.check(lib.fp_heads_to_nchw(_ptr(mh), _ptr(heads[('depth', hi)]), b, mh.shape[1], mh.shape[2], scale,
+                                            _ptr(out), stream))
+            outputs[key] = out
+        sv['s2d'] = s2d
+        sv['shape'] = (b, h, w)
+        self._saved = sv
+        return outputs
+
+    # ------------------------------------------------------------------------------ backward pieces
+    def _wgrad(self, L, src0, src1, dz, grads, stream):
+        """dW (and db) of one convolution from its gathered input and dZ [B][ho][wo][ld]."""
+        b, ho, wo, ld = dz.shape
+        d = self._desc(L, src0, src1, ho, wo)
+        need = self.lib.fp_conv_wgrad_workspace_bytes(ctypes.byref(d))
+        if self._wg_ws is None or self._wg_ws.numel() * 4 < need:
+            self._wg_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=dz.device)
+        dw = torch.empty(L.weight.shape, dtype=torch.float32, device=dz.device)
+        _lib.check(self.lib.fp_conv_wgrad(ctypes.byref(d), _ptr(src0), _ptr(src1), _ptr(dz), ld, self.gfmt,
+                                          1 if L.stem else 0, 0, _ptr(dw), _ptr(self._wg_ws), stream))
+        grads[L.weight] = dw
+        if L.bias is not None:
+            db = torch.empty(ld, dtype=torch.float32, device=dz.device)
+            _lib.check(self.lib.fp_bias_grad(_ptr(dz), b * ho * wo, ld, self.gfmt, _ptr(db), _ptr(self._reduce_ws()), stream))
+            grads[L.bias] = db[:L.cout] if ld != L.cout else db
+
+    def _dgrad_full(self, L, dz, stream):
+        """Gradient of the reflection-padded virtual input: zero-padded full correlation of dZ with the rotated
+        filter -> [B][ho+2][wo+2][cin] (decoder convs are 3x3 stride 1)."""
+        b, ho, wo, ld = dz.shape
+        cin = L.cin0 + L.cin1
+        out = torch.empty((b, ho + 2, wo + 2, cin), dtype=self.gdtype, device=dz.device)
+        d = FpConvDesc()
+        d.batch, d.c0, d.h0, d.w0, d.up0, d.c1 = b, ld, ho, wo, 0, 0
+        d.kh = d.kw = 3
+        d.stride, d.pad_t, d.pad_l, d.pad_mode = 1, 2, 2, FP_PAD_ZERO
+        d.ho, d.wo = ho + 2, wo + 2
+        d.cout, d.kpad, d.npad, d.bn = cin, L.d_kpad, L.d_npad, L.d_bn
+        d.act, d.dtype, d.out_f32, d.out_ld, d.res_ld, d.b_via_tma = FP_ACT_NONE, self.gfmt, 0, cin, 0, 1
+        assert ld == L.cpad_out, (L.name, ld, L.cpad_out)
+        _lib.check(self.lib.fp_conv_fwd(ctypes.byref(d), _ptr(dz), None, _ptr(L.w_flip), None, None, None, _ptr(out), stream))
+        return out
+
+    def _dgrad_plain(self, L, dz, out_hw, residual, stream):
+        """Encoder data gradient (zero padding): stride-1 convs are a plain correlation with the rotated filter,
+        stride-2 convs gather from the zero-inserted dZ (up0 = 2)."""
+        b, ho, wo, ld = dz.shape
+        cin = L.cin0
+        H, W = out_hw
+        out = torch.empty((b, H, W, cin), dtype=self.gdtype, device=dz.device)
+        d = FpConvDesc()
+        d.batch, d.c0, d.h0, d.w0, d.c1 = b, ld, ho, wo, 0
+        d.up0 = 2 if L.stride == 2 else 0
+        d.kh = d.kw = L.k
+        d.stride, d.pad_mode = 1, FP_PAD_ZERO
+        d.pad_t = d.pad_l = L.k - 1 - L.pad
+        d.ho, d.wo = H, W
+        d.cout, d.kpad, d.npad, d.bn = cin, L.d_kpad, L.d_npad, L.d_bn
+        d.act, d.dtype, d.out_f32, d.out_ld, d.b_via_tma = FP_ACT_NONE, self.gfmt, 0, cin, 1
+        d.res_ld = cin if residual is not None else 0
+        _lib.check(self.lib.fp_conv_fwd(ctypes.byref(d), _ptr(dz), None, _ptr(L.w_flip), None, None, _ptr(residual),
+                                        _ptr(out), stream))
+        return out
+
+    def _fold(self, dvp, hv, wv, coff, c, up, dst, accumulate, y_act, act, stream):
+        b = dvp.shape[0]
+        _lib.check(self.lib.fp_fold_bwd(_ptr(dvp), b, hv, wv, dvp.shape[3], coff, c, 1 if up else 0, 1 if accumulate else 0,
+                                        _ptr(y_act), act, self.fmt, self.gfmt, _ptr(dst), stream))
+
+    def _bn_bwd(self, L, dy, relu, want_g, grads, stream):
+        src, z, y = self._saved[L.name]
+        st = self._bn_state[L.name]
+        b, ho, wo, c = z.shape
+        dz = torch.empty(z.shape, dtype=self.gdtype, device=z.device)
+        g = torch.empty(z.shape, dtype=self.gdtype, device=z.device) if want_g else None
+        dgamma = torch.empty(c, dtype=torch.float32, device=z.device)
+        dbeta = torch.empty(c, dtype=torch.float32, device=z.device)
+        _lib.check(self.lib.fp_bn_bwd(_ptr(dy), _ptr(y), _ptr(z), _ptr(L.bn.weight.detach()), _ptr(st['mean']),
+                                      _ptr(st['invstd']), 1 if relu else 0, b * ho * wo, c, self.fmt, self.gfmt, _ptr(dz),
+                                      _ptr(g), _ptr(dgamma), _ptr(dbeta), _ptr(self._reduce_ws()), stream))
+        grads[L.bn.weight] = dgamma
+        grads[L.bn.bias] = dbeta
+        return dz, g
+
+    # ------------------------------------------------------------------------------ backward
+    def backward(self, douts):
+        """douts: {'1/8','1/4','1/2','1/1'} -> d(loss)/d(output) fp32 [B,4,H,W].  Returns {parameter: fp32 grad}."""
+        sv = self._saved
+        if sv is None:
+            raise RuntimeError('backward() without a preceding forward_train()')
+        b, h, w = sv['shape']
+        stream = self._stream()
+        lib = self.lib
+        dev = self._dev()
+        grads = {}
+        feats = sv['feats']
+        dfeat = [None] * 5          # gradient accumulators of the encoder features f0..f4 (from the decoders)
+
+        def gnew(shape):
+            return torch.empty(shape, dtype=self.gdtype, device=dev)
+
+        for dname in ('mask', 'depth'):
+            d = self.dec[dname]
+            ch0 = 0 if dname == 'mask' else 2
+            sigmoid = d['head4'].act != FP_ACT_NONE
+
+            def head_dz(hi):
+                L = d[f'head{hi}']
+                src, _, hd = sv[L.name]
+                hh, ww = hd.shape[1], hd.shape[2]
+                dz = gnew((b, hh, ww, 8))
+                _lib.check(lib.fp_heads_bwd(_ptr(douts[SCALES[hi - 1]]), ch0, _ptr(hd) if sigmoid else None, b, hh, ww,
+                                            h // hh, self.gfmt, _ptr(dz), stream))
+                return L, src, dz
+
+            def conv_bwd(L, dz):
+                """wgrad + full dgrad of a decoder conv; returns the padded virtual-input gradient."""
+                src0, src1, _ = sv[L.name]
+                self._wgrad(L, src0, src1, dz, grads, stream)
+                return self._dgrad_full(L, dz, stream)
+
+            # ---- outconv4 chain at full resolution
+            L, src, dz = head_dz(4)
+            dvp = conv_bwd(L, dz)
+            o4c2_out = src
+            dz = gnew(o4c2_out.shape)
+            self._fold(dvp, h, w, 0, 32, False, dz, False, o4c2_out, FP_ACT_ELU, stream)
+            L = d['o4.c2']
+            dvp = conv_bwd(L, dz)
+            o4c1_out = sv[L.name][0]
+            dz = gnew(o4c1_out.shape)
+            self._fold(dvp, h, w, 0, 32, False, dz, False, o4c1_out, FP_ACT_ELU, stream)
+            L = d['o4.c1']
+            dvp = conv_bwd(L, dz)
+            x = sv[L.name][0]                       # block4 output [b, h/2, w/2, 64]
+            dx = gnew(x.shape)
+            self._fold(dvp, h, w, 0, 64, True, dx, False, None, FP_ACT_NONE, stream)
+            del dvp, dz
+            # ---- blocks 4..1 (each block output also feeds a head, except block1)
+            for bi in range(4, 0, -1):
+                hh, ww = x.shape[1], x.shape[2]
+                co = x.shape[3]
+                if bi >= 2:
+                    L, src, dzh = head_dz(bi - 1)
+                    dvp = conv_bwd(L, dzh)
+                    self._fold(dvp, hh, ww, 0, co, False, dx, True, x, FP_ACT_ELU, stream)     # + head path, then ELU'
+                    dz = dx
+                else:
+                    dz = gnew(x.shape)
+                    _lib.check(lib.fp_act_bwd(_ptr(dx), _ptr(x), FP_ACT_ELU, x.numel(), self.fmt, self.gfmt, _ptr(dz), stream))
+                L = d[f'b{bi}.post2']
+                dvp = conv_bwd(L, dz)
+                t3 = sv[L.name][0]
+                dz = gnew(t3.shape)
+                self._fold(dvp, hh, ww, 0, co, False, dz, False, t3, FP_ACT_ELU, stream)
+                L = d[f'b{bi}.post1']
+                dvp = conv_bwd(L, dz)
+                t2, skip, _ = sv[L.name]
+                dz = gnew(t2.shape)
+                self._fold(dvp, hh, ww, 0, co, True, dz, False, t2, FP_ACT_ELU, stream)          # upsampled half
+                fi = 4 - bi
+                if dfeat[fi] is None:
+                    dfeat[fi] = gnew(skip.shape)
+                    self._fold(dvp, hh, ww, co, skip.shape[3], False, dfeat[fi], False, None, FP_ACT_NONE, stream)
+                else:
+                    self._fold(dvp, hh, ww, co, skip.shape[3], False, dfeat[fi], True, None, FP_ACT_NONE, stream)
+                L = d[f'b{bi}.pre2']
+                dvp = conv_bwd(L, dz)
+                t = sv[L.name][0]
+                dz = gnew(t.shape)
+                self._fold(dvp, hh // 2, ww // 2, 0, co, False, dz, False, t, FP_ACT_ELU, stream)
+                L = d[f'b{bi}.pre1']
+                dvp = conv_bwd(L, dz)
+                x = sv[L.name][0]                   # previous block output, or f4 for block1
+                if bi >= 2:
+                    dx = gnew(x.shape)
+                    self._fold(dvp, hh // 2, ww // 2, 0, x.shape[3], False, dx, False, None, FP_ACT_NONE, stream)
+                else:
+                    if dfeat[4] is None:
+                        dfeat[4] = gnew(x.shape)
+                        self._fold(dvp, hh // 2, ww // 2, 0, x.shape[3], False, dfeat[4], False, None, FP_ACT_NONE, stream)
+                    else:
+                        self._fold(dvp, hh // 2, ww // 2, 0, x.shape[3], False, dfeat[4], True, None, FP_ACT_NONE, stream)
+                del dvp
+
+        # ---- encoder, last block first.  dy = gradient of the current block's output.
+        dy = dfeat[4]
+        for idx in range(len(self.enc_blocks) - 1, -1, -1):
+            li, c1, ds, c2 = self.enc_blocks[idx]
+            x_in = sv[c1.name][0]
+            dz2, g = self._bn_bwd(c2, dy, True, True, grads, stream)
+            t1 = sv[c2.name][0]
+            self._wgrad(c2, t1, None, dz2, grads, stream)
+            dt1 = self._dgrad_plain(c2, dz2, (t1.shape[1], t1.shape[2]), None, stream)
+            dz1, _ = self._bn_bwd(c1, dt1, True, False, grads, stream)
+            self._wgrad(c1, x_in, None, dz1, grads, stream)
+            first_of_stage = idx == 0 or self.enc_blocks[idx - 1][0] != li
+            if ds is not None:
+                dzd, _ = self._bn_bwd(ds, g, False, False, grads, stream)
+                self._wgrad(ds, x_in, None, dzd, grads, stream)
+                # the block input is the previous stage's feature: add the decoders' contribution here
+                extra = dfeat[li] if first_of_stage else None
+                dres = self._dgrad_plain(ds, dzd, (x_in.shape[1], x_in.shape[2]), extra, stream)
+            else:
+                dres = g
+            dy = self._dgrad_plain(c1, dz1, (x_in.shape[1], x_in.shape[2]), dres, stream)
+            del dz2, g, dt1, dz1
+        # dy is now the gradient of the max-pool output; f0 also received gradient from the decoders
+        f0 = feats[0]
+        if dfeat[0] is None:
+            dfeat[0] = torch.zeros(f0.shape, dtype=self.gdtype, device=dev)
+        _lib.check(lib.fp_maxpool3x3s2_bwd(_ptr(f0), _ptr(dy), b, f0.shape[1], f0.shape[2], 64, self.fmt, self.gfmt, 1,
+                                           _ptr(dfeat[0]), stream))
+        stem = self.layers['stem']
+        dz0, _ = self._bn_bwd(stem, dfeat[0], True, False, grads, stream)
+        self._wgrad(stem, sv['s2d'], None, dz0, grads, stream)
+        self._saved = None
+        return grads

@@ -50,7 +50,9 @@ int fp_check_device(void);
 typedef struct FpConvDesc {
   int32_t batch;
   int32_t c0, h0, w0; /* source 0: channels, stored height/width                                  */
-  int32_t up0;        /* 1: source 0 is nearest-upsampled x2 (virtual input = 2*h0 x 2*w0)        */
+  int32_t up0;        /* 1: source 0 is nearest-upsampled x2 (virtual input = 2*h0 x 2*w0);
+                         2: source 0 is zero-inserted x2 — the data gradient of a stride-2 convolution
+                            expressed as a stride-1 gather (c1 = 0, zero padding only)                 */
   int32_t c1;         /* source 1 channels (0 = no concat); stored at the virtual input size      */
   int32_t kh, kw, stride, pad_t, pad_l;
   int32_t pad_mode;   /* FP_PAD_ZERO / FP_PAD_REFLECT                                             */
@@ -65,17 +67,20 @@ typedef struct FpConvDesc {
   int32_t out_ld;     /* output row stride in elements                                            */
   int32_t res_ld;     /* residual row stride in elements                                          */
   int32_t b_via_tma;  /* 1: weights by TMA (default); 0: weights by cp.async (debug)              */
+  int32_t w_dtype_plus1; /* 0: weights have `dtype`; otherwise weight format + 1 (mixed f16 x bf16)       */
 } FpConvDesc;
 
 int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* src1, const void* w_packed,
                 const float* scale, const float* shift, const void* residual, void* out, void* stream);
 
-/* OIHW fp32 -> packed [npad][kpad] 16-bit, K index = (ky*kw + kx)*cin + c (tap-major, channel-minor),
- * zero padded.  flip=1 packs the dgrad operand instead: rows = cin, K = (ky*kw+kx)*cout + co with the
- * filter rotated by 180 degrees.  Replaces nothing in the reference (weights there stay OIHW fp32 for
- * cuDNN); it is the layout the UMMA descriptors of fp_conv_fwd expect. */
-int fp_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int npad, int kpad, int dtype,
-                        int flip, void* w_packed, void* stream);
+/* OIHW fp32 -> packed [npad][kpad] 16-bit, K index = (ky*kw + kx)*cpad + c (tap-major, channel-minor),
+ * zero padded; cpad >= the channel-minor extent (cin, or cout when flipped) is the channel count of the
+ * tensor the kernel will gather (a power of two >= 8 together with a concat partner).  flip=1 packs the
+ * dgrad operand instead: rows = cin, K = (ky*kw+kx)*cpad + co with the filter rotated by 180 degrees.
+ * Replaces nothing in the reference (weights there stay OIHW fp32 for cuDNN); it is the layout the UMMA
+ * descriptors of fp_conv_fwd expect. */
+int fp_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int cpad, int npad, int kpad,
+                        int dtype, int flip, void* w_packed, void* stream);
 
 /* Stem weight [64][3][7][7] -> packed [npad][256] for the space-to-depth formulation: the 7x7/2 conv
  * (torchvision resnet.py:197) equals a 4x4/1 conv over 2x2 space-to-depth blocks of 16 channels
@@ -94,6 +99,82 @@ int fp_maxpool3x3s2(const void* in, int batch, int h, int w, int c, int dtype, v
  * (torch.cat([mask, depth], 1), network.py:27-28).  scale 1 is a plain layout change. */
 int fp_heads_to_nchw(const float* mask_head, const float* depth_head, int batch, int h, int w, int scale,
                      float* out_nchw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training step.  Replaces autograd's backward of footprints/network.py (triggered at
+ * footprints/training/train.py:155), train-mode BatchNorm (torchvision resnet.py:82-104 in .train()),
+ * LossManager (footprints/training/losses.py:31-152) and Adam (footprints/model_manager.py:27).
+ * Gradients flowing between layers are 16-bit (`grad_dtype`, bf16 by default for range); weight, bias
+ * and BatchNorm gradients are fp32.  Every reduction is two-stage with a fixed summation order.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* floats of scratch the column-reduction kernels (bn_stats / bn_bwd / bias_grad) need for C channels */
+int fp_reduce_workspace_floats(int C);
+
+/* Train-mode BatchNorm2d statistics of a conv output z [M][C]: batch mean / biased variance -> scale, shift
+ * (y = z*scale + shift), saved mean / invstd for backward, and the running-stat update (momentum, unbiased
+ * variance) exactly as torch.nn.functional.batch_norm(training=True).  running_* may be NULL. */
+int fp_bn_stats(const void* z, long long M, int C, int dtype, const float* gamma, const float* beta,
+                float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                float* save_mean, float* save_invstd, float* workspace, void* stream);
+
+/* y = [relu](z*scale[c] + shift[c] (+ residual)) — BatchNorm apply + residual add + ReLU (resnet.py:92-104). */
+int fp_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, int relu, long long M,
+                int C, int dtype, void* y, void* stream);
+
+/* BatchNorm backward with the following ReLU folded in: g = dy*(y>0) (relu=1) or dy; dgamma, dbeta (fp32);
+ * dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)).  g_out (nullable) receives g, the gradient of the
+ * residual branch. */
+int fp_bn_bwd(const void* dy, const void* y, const void* z, const float* gamma, const float* save_mean,
+              const float* save_invstd, int relu, long long M, int C, int act_dtype, int grad_dtype, void* dz,
+              void* g_out, float* dgamma, float* dbeta, float* workspace, void* stream);
+
+/* dbias[c] = sum_m dz[m][c] (Conv2d bias gradient). */
+int fp_bias_grad(const void* dz, long long M, int C, int grad_dtype, float* dbias, float* workspace, void* stream);
+
+/* LossManager.__call__ (losses.py:31-92) fused with its gradient.  pred[4]: the '1/8','1/4','1/2','1/1'
+ * outputs [B][4][H][W] fp32; targets [B][H][W] fp32.  losses21: per scale {visible_ground, all_ground, depth,
+ * ground_depth, their sum} then [20] = mean over scales.  grad (nullable) receives d(loss)/d(pred) for each scale.
+ * workspace: 1184*16 floats. */
+int fp_loss_fwd_bwd(const float* const* pred, float* const* grad, const float* depth, const float* visible,
+                    const float* all_ground, const float* ground_depth, const float* moving, const float* depth_mask,
+                    int batch, int h, int w, float min_depth, float max_depth, float prior_weight, float* losses21,
+                    float* workspace, void* stream);
+
+/* Adjoint of fp_heads_to_nchw for one decoder: channels [ch0, ch0+2) of dout [B][4][H][W] -> gradient of the head
+ * convolution's pre-upsample output [B][h][w][8] (channels 2..7 zero), times sigmoid' when head_post (the saved
+ * post-sigmoid head map) is given (network.py:177-181). */
+int fp_heads_bwd(const float* dout_nchw, int ch0, const float* head_post, int batch, int h, int w, int scale,
+                 int grad_dtype, void* dz8, void* stream);
+
+/* Adjoint of [nearest x2] -> [concat] -> [ReflectionPad2d(1)] (network.py:154-155,115): folds the gradient of the
+ * padded virtual input dvp [B][hv+2][wv+2][ccat] (produced by fp_conv_fwd run as a zero-padded full correlation
+ * with the flipped weights) onto one source: channels [coff, coff+c); up=1 sums the 2x2 upsample replicas.
+ * Optionally accumulates into dst and multiplies by the producing layer's activation derivative from its saved
+ * output y_act (ELU: y>0 ? 1 : y+1, ReLU: y>0). */
+int fp_fold_bwd(const void* dvp, int batch, int hv, int wv, int ccat, int coff, int c, int up, int accumulate,
+                const void* y_act, int act, int act_dtype, int grad_dtype, void* dst, void* stream);
+
+/* dz = dy * act'(y), n elements (multiple of 8). */
+int fp_act_bwd(const void* dy, const void* y, int act, long long n, int act_dtype, int grad_dtype, void* dz,
+               void* stream);
+/* a += b on 16-bit gradient buffers, n elements (multiple of 8). */
+int fp_grad_add(void* a, const void* b, long long n, int grad_dtype, void* stream);
+/* MaxPool2d(3,2,1) backward (first maximum wins ties). */
+int fp_maxpool3x3s2_bwd(const void* x, const void* dy, int batch, int h, int w, int c, int act_dtype, int grad_dtype,
+                        int accumulate, void* dx, void* stream);
+
+/* Weight gradient of the convolution described by d (same gather as fp_conv_fwd) on tensor cores:
+ * dw_oihw[co][ci][ky][kx] (+)= sum_m dz[m][co] * im2col(src)[m][(ky*kw+kx)*cin+ci].  stem=1: d is the 4x4
+ * space-to-depth stem and dw is the original [64][3][7][7] filter. */
+long long fp_conv_wgrad_workspace_bytes(const FpConvDesc* d);
+int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* src1, const void* dz, int dz_ld, int grad_dtype,
+                  int stem, int accumulate, float* dw_oihw, float* workspace, void* stream);
+
+/* torch.optim.Adam step (no weight decay / amsgrad) over a flat fp32 buffer; step is 1-based;
+ * grad_scale multiplies the gradient first (1/world_size after a summing all-reduce). */
+int fp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                 float beta2, float eps, int step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,7 @@ def test_single_conv_c_abi_vs_torch_fp32(cfg):
     npad = (cfg['cout'] + bn_tile - 1) // bn_tile * bn_tile
     kpad = (cfg['k'] ** 2 * cin + 63) // 64 * 64
     wp = torch.empty(npad, kpad, dtype=torch.float16, device='cuda')
-    _lib.check(lib.fp_pack_conv_weight(w.data_ptr(), cfg['cout'], cin, cfg['k'], cfg['k'], npad, kpad, 0, 0,
+    _lib.check(lib.fp_pack_conv_weight(w.data_ptr(), cfg['cout'], cin, cfg['k'], cfg['k'], cin, npad, kpad, 0, 0,
                                        wp.data_ptr(), None))
     ho = (hin + 2 * cfg['pad'] - cfg['k']) // cfg['stride'] + 1
     wo = (win + 2 * cfg['pad'] - cfg['k']) // cfg['stride'] + 1

@@ -1,0 +1,146 @@
+"""GPU parity of the training step (train-mode forward, fused loss, hand-written backward) against the CPU
+oracle (oracle/footprints_oracle.py) and the reference fixtures.  Activations and inter-layer gradients are
+bf16 on our side, fp32 in the reference, so parameter gradients are compared by direction (cosine) and norm."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from footprints_b200 import FootprintNetwork, LossManager
+from footprints_b200.losses import fused_loss
+from footprints_b200.synthetic import synthetic_batch, synthetic_state_dict
+from oracle import footprints_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+BLOCKS = {'resnet34': (3, 4, 6, 3), 'resnet18': (2, 2, 2, 2)}
+
+
+def _net(arch):
+    net = FootprintNetwork(pretrained=False, blocks=BLOCKS[arch])
+    net.load_state_dict(synthetic_state_dict(arch, 0))
+    return net.cuda().train()
+
+
+def test_fused_loss_matches_oracle_and_autograd():
+    g = torch.Generator().manual_seed(11)
+    b, h, w = 2, 64, 96
+    data = synthetic_batch(b, h, w, 3)
+    preds = [torch.randn(b, 4, h, w, generator=g) for _ in range(4)]
+    for p in preds:
+        p[:, 2:4] = torch.sigmoid(p[:, 2:4])
+    ref_in = {k: p.clone().requires_grad_(True) for k, p in zip(O.SCALES, preds)}
+    ref = O.loss_forward(ref_in, data)
+    ref['loss'].backward()
+    tg = {k: v.cuda() for k, v in data.items() if k != 'image'}
+    out, grads = fused_loss([p.cuda() for p in preds], tg, (0.1, 100.0), 0.25, True)
+    out = out.cpu()
+    terms = ('visible_ground', 'all_ground', 'depth', 'ground_depth', 'loss')
+    for s, k in enumerate(O.SCALES):
+        for c, t in enumerate(terms):
+            assert abs(out[5 * s + c].item() - ref[(t, k)].item()) <= 2e-6 * max(1.0, abs(ref[(t, k)].item())), (t, k)
+    assert abs(out[20].item() - ref['loss'].item()) <= 2e-6 * abs(ref['loss'].item())
+    for s, k in enumerate(O.SCALES):
+        gr = ref_in[k].grad
+        assert (grads[s].cpu() - gr).abs().max() <= 1e-5 * gr.abs().max() + 1e-12
+
+
+def test_loss_manager_contract_matches_reference_fixture():
+    """Keys, order and values of LossManager on the reference's own train-mode outputs are pinned by the fixture;
+    here: same keys/order, and values on our outputs close to the fixture's."""
+    gold = np.load(os.path.join(GOLD, 'ref_resnet34_b2_64x96.npz'))
+    net = _net('resnet34')
+    data = synthetic_batch(2, 64, 96, 1)
+    out = net(data['image'].cuda())
+    targets = {k: v.cuda() for k, v in data.items() if k != 'image'}
+    losses = LossManager((0.1, 100.0), 0.25)(out, targets)
+    keys = list(losses.keys())
+    expect = []
+    for k in O.SCALES:
+        expect += [('visible_ground', k), ('all_ground', k), ('depth', k), ('ground_depth', k), ('loss', k)]
+    expect.append('loss')
+    assert keys == expect
+    for k, v in losses.items():
+        name = 'loss/' + (k if isinstance(k, str) else f'{k[0]}@{k[1]}')
+        assert abs(v.item() - float(gold[name])) <= 2e-2 * max(1.0, abs(float(gold[name]))), (name, v.item(), float(gold[name]))
+    for key in (('visible_ground', '1/1'), ('all_ground', '1/1'), ('depth', '1/1'), ('ground_depth', '1/1'),
+                ('ground_depth_masked', '1/1')):
+        assert out[key].shape == (2, 64, 96)
+
+
+@pytest.mark.parametrize('arch', ['resnet34', 'resnet18'])
+def test_train_step_matches_oracle(arch):
+    sd = synthetic_state_dict(arch, 0)
+    data = synthetic_batch(2, 64, 96, 1)
+    ref_out, ref_losses, ref_grads, ref_stats = O.train_step_reference(sd, data, arch)
+    net = _net(arch)
+    out = net(data['image'].cuda())
+    for k in O.SCALES:
+        err = (out[k].detach().cpu() - ref_out[k].detach()).abs().max().item()
+        print(f'{arch} train fwd scale {k}: max abs err {err:.3e}')
+        assert err <= 5e-2, (k, err)                     # bf16 activations, batch-stat BN
+    targets = {k: v.cuda() for k, v in data.items() if k != 'image'}
+    losses = LossManager((0.1, 100.0), 0.25, side_outputs=False)(out, targets)
+    assert abs(losses['loss'].item() - ref_losses['loss'].item()) <= 1e-2 * ref_losses['loss'].item()
+    net.zero_grad()
+    losses['loss'].backward()
+    named = dict(net.named_parameters())
+    worst = (1.0, None)
+    for name, gref in ref_grads.items():
+        gours = named[name].grad
+        assert gours is not None, name
+        a, r = gours.detach().float().cpu().flatten(), gref.flatten()
+        assert torch.isfinite(a).all(), name
+        cos = torch.dot(a, r) / (a.norm() * r.norm() + 1e-30)
+        ratio = (a.norm() / (r.norm() + 1e-30)).item()
+        if cos.item() < worst[0]:
+            worst = (cos.item(), name)
+        assert cos.item() >= 0.97, (name, cos.item(), ratio)
+        assert 0.9 <= ratio <= 1.1, (name, cos.item(), ratio)
+    print(f'{arch}: worst gradient cosine {worst}')
+    # parameters that get no gradient in the reference get none here either (unused decoder BNs)
+    for name, p in named.items():
+        if name not in ref_grads:
+            assert p.grad is None, name
+    # running statistics were updated like torch BatchNorm2d(momentum=0.1)
+    new_sd = net.state_dict()
+    for k, v in ref_stats.items():
+        assert torch.allclose(new_sd[k].cpu(), v, rtol=2e-2, atol=2e-2), k
+    assert int(new_sd['encoder.layer0.1.num_batches_tracked']) == 1
+
+
+def test_train_step_reference_fixture_gradient_norms():
+    gold = np.load(os.path.join(GOLD, 'ref_resnet34_b2_64x96.npz'))
+    net = _net('resnet34')
+    data = synthetic_batch(2, 64, 96, 1)
+    out = net(data['image'].cuda())
+    targets = {k: v.cuda() for k, v in data.items() if k != 'image'}
+    LossManager((0.1, 100.0), 0.25, side_outputs=False)(out, targets)['loss'].backward()
+    named = dict(net.named_parameters())
+    for name, ref_norm in zip(gold['grad_names'], gold['grad_norms']):
+        n = named[str(name)].grad.double().norm().item()
+        assert abs(n - ref_norm) <= 0.1 * ref_norm + 1e-12, (str(name), n, ref_norm)
+        idx = torch.from_numpy(gold[f'grad/{name}/idx']).long()
+        ref = torch.from_numpy(gold[f'grad/{name}/val'])
+        got = named[str(name)].grad.flatten().cpu()[idx]
+        assert (got - ref).abs().max() <= 0.25 * ref.abs().max() + 1e-9, str(name)
+
+
+def test_optimizer_step_through_reference_training_loop_surface():
+    """model.zero_grad(); losses['loss'].backward(); optimiser.step() as in footprints/training/train.py:153-156."""
+    from footprints_b200 import ModelManager
+    mm = ModelManager(use_cuda=True, is_inference=False, pretrained=False, learning_rate=1e-4)
+    mm.model.train()
+    data = synthetic_batch(2, 64, 96, 4)
+    targets = {k: v.cuda() for k, v in data.items() if k != 'image'}
+    lm = LossManager((0.1, 100.0), 0.25)
+    first = None
+    for _ in range(3):
+        out = mm.model(data['image'].cuda())
+        losses = lm(out, targets)
+        mm.model.zero_grad()
+        losses['loss'].backward()
+        mm.optimiser.step()
+        first = first if first is not None else losses['loss'].item()
+    assert losses['loss'].item() < first          # three Adam steps on one batch reduce its loss
