@@ -25,6 +25,17 @@ RESNET_BLOCKS = {'resnet18': (2, 2, 2, 2), 'resnet34': (3, 4, 6, 3)}
 SCALES = ('1/8', '1/4', '1/2', '1/1')
 
 
+def _q(x, qdtype):
+    """Optional storage-precision emulation (NOT part of the reference): round to the CUDA path's 16-bit
+    storage type with a straight-through gradient.  With ``qdtype=None`` (default) the oracle is the fp32
+    reference arithmetic.  Used by the gradient-parity tests so that ReLU/ELU masks are evaluated at the same
+    point as on the GPU; a ReLU network's gradient is piecewise constant, so comparing against the fp32
+    forward would measure forward rounding (mask flips), not the backward kernels."""
+    if qdtype is None:
+        return x
+    return x + (x.to(qdtype).to(x.dtype) - x).detach()
+
+
 def _bn(sd, prefix, x, training, new_stats):
     """torch BatchNorm2d, eps 1e-5, momentum 0.1 (torchvision resnet.py:82 default norm_layer)."""
     w, b = sd[f'{prefix}.weight'], sd[f'{prefix}.bias']
@@ -39,12 +50,13 @@ def _bn(sd, prefix, x, training, new_stats):
     return F.batch_norm(x, rm, rv, w, b, False, 0.1, 1e-5)
 
 
-def encoder_forward(sd, image, arch='resnet34', training=False, new_stats=None, taps=None):
+def encoder_forward(sd, image, arch='resnet34', training=False, new_stats=None, taps=None, qdtype=None):
     """ResnetEncoder.forward — footprints/network.py:48-59; BasicBlock torchvision resnet.py:59-106."""
     blocks = RESNET_BLOCKS[arch]
-    x = (image - 0.45) / 0.225                                               # network.py:50
-    x = F.conv2d(x, sd['encoder.layer0.0.weight'], None, stride=2, padding=3)  # :52 (conv1)
-    x = F.relu(_bn(sd, 'encoder.layer0.1', x, training, new_stats))
+    q = lambda t: _q(t, qdtype)                                              # identity unless emulating storage
+    x = q((image - 0.45) / 0.225)                                            # network.py:50
+    x = q(F.conv2d(x, q(sd['encoder.layer0.0.weight']), None, stride=2, padding=3))  # :52 (conv1)
+    x = q(F.relu(_bn(sd, 'encoder.layer0.1', x, training, new_stats)))
     feats = [x]
     x = F.max_pool2d(x, 3, 2, 1)                                             # layer1[0] = maxpool
     for li, nb in enumerate(blocks):
@@ -53,40 +65,40 @@ def encoder_forward(sd, image, arch='resnet34', training=False, new_stats=None, 
             p = f'{base}.{b}'
             stride = 2 if (b == 0 and li > 0) else 1
             idt = x
-            out = F.conv2d(x, sd[f'{p}.conv1.weight'], None, stride=stride, padding=1)
-            out = F.relu(_bn(sd, f'{p}.bn1', out, training, new_stats))
-            out = F.conv2d(out, sd[f'{p}.conv2.weight'], None, stride=1, padding=1)
+            out = q(F.conv2d(x, q(sd[f'{p}.conv1.weight']), None, stride=stride, padding=1))
+            out = q(F.relu(_bn(sd, f'{p}.bn1', out, training, new_stats)))
+            out = q(F.conv2d(out, q(sd[f'{p}.conv2.weight']), None, stride=1, padding=1))
             out = _bn(sd, f'{p}.bn2', out, training, new_stats)
             if f'{p}.downsample.0.weight' in sd:
-                idt = F.conv2d(x, sd[f'{p}.downsample.0.weight'], None, stride=2)
-                idt = _bn(sd, f'{p}.downsample.1', idt, training, new_stats)
-            x = F.relu(out + idt)
+                idt = q(F.conv2d(x, q(sd[f'{p}.downsample.0.weight']), None, stride=2))
+                idt = q(_bn(sd, f'{p}.downsample.1', idt, training, new_stats))
+            x = q(F.relu(out + idt))
             if taps is not None:
                 taps[p] = x
         feats.append(x)
     return feats
 
 
-def _conv_block(sd, p, x):
+def _conv_block(sd, p, x, qdtype=None):
     """ConvBlock.forward with use_bn=False, ELU — footprints/network.py:124-138."""
     for i in (1, 2):
         x = F.pad(x, (1, 1, 1, 1), mode='reflect')
-        x = F.elu(F.conv2d(x, sd[f'{p}.conv{i}.weight'], sd[f'{p}.conv{i}.bias']))
+        x = _q(F.elu(F.conv2d(x, _q(sd[f'{p}.conv{i}.weight'], qdtype), sd[f'{p}.conv{i}.bias'])), qdtype)
     return x
 
 
-def _up_block(sd, p, x, skip):
+def _up_block(sd, p, x, skip, qdtype=None):
     """ConvUpsampleAndConcatBlock.forward — footprints/network.py:151-158."""
-    x = _conv_block(sd, f'{p}.pre_concat_conv', x)
+    x = _conv_block(sd, f'{p}.pre_concat_conv', x, qdtype)
     x = F.interpolate(x, scale_factor=2, mode='nearest')
     x = torch.cat([x, skip], 1)
-    return _conv_block(sd, f'{p}.post_concat_conv', x)
+    return _conv_block(sd, f'{p}.post_concat_conv', x, qdtype)
 
 
-def _out_conv(sd, p, x, scale, apply_sigmoid):
+def _out_conv(sd, p, x, scale, apply_sigmoid, qdtype=None):
     """OutConvBlock.forward — footprints/network.py:174-183."""
     x = F.pad(x, (1, 1, 1, 1), mode='reflect')
-    x = F.conv2d(x, sd[f'{p}.conv1.weight'], sd[f'{p}.conv1.bias'])
+    x = F.conv2d(x, _q(sd[f'{p}.conv1.weight'], qdtype), sd[f'{p}.conv1.bias'])
     if apply_sigmoid:
         x = torch.sigmoid(x)
     if scale != 1:
@@ -94,33 +106,33 @@ def _out_conv(sd, p, x, scale, apply_sigmoid):
     return x
 
 
-def decoder_forward(sd, dec, feats, apply_sigmoid, taps=None):
+def decoder_forward(sd, dec, feats, apply_sigmoid, taps=None, qdtype=None):
     """SkipDecoder.forward — footprints/network.py:82-101."""
     out = OrderedDict()
-    x = _up_block(sd, f'{dec}.block1', feats[-1], feats[-2])
-    x = _up_block(sd, f'{dec}.block2', x, feats[-3])
-    out['1/8'] = _out_conv(sd, f'{dec}.outconv1', x, 8, apply_sigmoid)
-    x = _up_block(sd, f'{dec}.block3', x, feats[-4])
-    out['1/4'] = _out_conv(sd, f'{dec}.outconv2', x, 4, apply_sigmoid)
-    x = _up_block(sd, f'{dec}.block4', x, feats[-5])
+    x = _up_block(sd, f'{dec}.block1', feats[-1], feats[-2], qdtype)
+    x = _up_block(sd, f'{dec}.block2', x, feats[-3], qdtype)
+    out['1/8'] = _out_conv(sd, f'{dec}.outconv1', x, 8, apply_sigmoid, qdtype)
+    x = _up_block(sd, f'{dec}.block3', x, feats[-4], qdtype)
+    out['1/4'] = _out_conv(sd, f'{dec}.outconv2', x, 4, apply_sigmoid, qdtype)
+    x = _up_block(sd, f'{dec}.block4', x, feats[-5], qdtype)
     if taps is not None:
         taps[f'{dec}.block4'] = x
-    out['1/2'] = _out_conv(sd, f'{dec}.outconv3', x, 2, apply_sigmoid)
+    out['1/2'] = _out_conv(sd, f'{dec}.outconv3', x, 2, apply_sigmoid, qdtype)
     x = F.interpolate(x, scale_factor=2, mode='nearest')
-    x = _conv_block(sd, f'{dec}.outconv4.0', x)
-    out['1/1'] = _out_conv(sd, f'{dec}.outconv4.1', x, 1, apply_sigmoid)
+    x = _conv_block(sd, f'{dec}.outconv4.0', x, qdtype)
+    out['1/1'] = _out_conv(sd, f'{dec}.outconv4.1', x, 1, apply_sigmoid, qdtype)
     return out
 
 
-def network_forward(sd, image, arch='resnet34', training=False, new_stats=None, taps=None):
+def network_forward(sd, image, arch='resnet34', training=False, new_stats=None, taps=None, qdtype=None):
     """FootprintNetwork.forward — footprints/network.py:21-30.  Returns OrderedDict of four
     [B,4,H,W] tensors keyed '1/8','1/4','1/2','1/1' (that insertion order)."""
-    feats = encoder_forward(sd, image, arch, training, new_stats, taps)
+    feats = encoder_forward(sd, image, arch, training, new_stats, taps, qdtype)
     if taps is not None:
         for i, f in enumerate(feats):
             taps[f'f{i}'] = f
-    mask = decoder_forward(sd, 'mask_decoder', feats, False, taps)
-    depth = decoder_forward(sd, 'depth_decoder', feats, True, taps)
+    mask = decoder_forward(sd, 'mask_decoder', feats, False, taps, qdtype)
+    depth = decoder_forward(sd, 'depth_decoder', feats, True, taps, qdtype)
     return OrderedDict((k, torch.cat([mask[k], depth[k]], 1)) for k in mask)
 
 
@@ -165,7 +177,7 @@ def loss_forward(predictions, targets, depth_range=(0.1, 100.0), prior_weight=0.
     return losses
 
 
-def train_step_reference(sd, batch, arch='resnet34', depth_range=(0.1, 100.0), prior_weight=0.25):
+def train_step_reference(sd, batch, arch='resnet34', depth_range=(0.1, 100.0), prior_weight=0.25, qdtype=None):
     """One forward(train-mode BN) + loss + backward (autograd over this restatement), i.e. the
     arithmetic of footprints/training/train.py:153-155,224-225.  Returns (outputs, losses, grads,
     new_running_stats).  Parameters that never receive a gradient (the unused decoder BNs,
@@ -177,7 +189,7 @@ def train_step_reference(sd, batch, arch='resnet34', depth_range=(0.1, 100.0), p
         else:
             params[k] = v
     new_stats = {}
-    outs = network_forward(params, batch['image'], arch, True, new_stats)
+    outs = network_forward(params, batch['image'], arch, True, new_stats, qdtype=qdtype)
     losses = loss_forward(outs, batch, depth_range, prior_weight)
     losses['loss'].backward()
     grads = OrderedDict((k, v.grad) for k, v in params.items()

@@ -71,9 +71,19 @@ def test_loss_manager_contract_matches_reference_fixture():
 
 @pytest.mark.parametrize('arch', ['resnet34', 'resnet18'])
 def test_train_step_matches_oracle(arch):
+    """Forward, loss and BatchNorm running statistics against the fp32 oracle; parameter gradients by direction
+    and norm.
+
+    A ReLU/BatchNorm network's gradient is piecewise constant in its activations, so 16-bit storage rounding
+    (which flips ~1 % of the ReLU masks per layer) bounds the attainable agreement: inside the CPU oracle itself,
+    bf16-storage emulation vs fp32 gives cosines of only 0.84-0.95 for the deep encoder weights on this input, and
+    two emulated runs whose inputs differ by 1e-6 agree to 0.89-0.95.  The per-parameter
+    bar is therefore: at least as close to the storage-emulating oracle as that oracle is to fp32 (minus 0.03), and
+    norms within 10 %.  The backward kernels themselves are pinned tightly, op by op, in test_gpu_train_kernels.py."""
     sd = synthetic_state_dict(arch, 0)
     data = synthetic_batch(2, 64, 96, 1)
-    ref_out, ref_losses, ref_grads, ref_stats = O.train_step_reference(sd, data, arch)
+    ref_out, ref_losses, g32, ref_stats = O.train_step_reference(sd, data, arch)
+    _, _, gq, _ = O.train_step_reference(sd, data, arch, qdtype=torch.bfloat16)
     net = _net(arch)
     out = net(data['image'].cuda())
     for k in O.SCALES:
@@ -86,22 +96,28 @@ def test_train_step_matches_oracle(arch):
     net.zero_grad()
     losses['loss'].backward()
     named = dict(net.named_parameters())
+
+    def cosine(a, r):
+        return (torch.dot(a, r) / (a.norm() * r.norm() + 1e-30)).item()
+
     worst = (1.0, None)
-    for name, gref in ref_grads.items():
+    for name, gref in gq.items():
         gours = named[name].grad
         assert gours is not None, name
         a, r = gours.detach().float().cpu().flatten(), gref.flatten()
         assert torch.isfinite(a).all(), name
-        cos = torch.dot(a, r) / (a.norm() * r.norm() + 1e-30)
+        cos = cosine(a, r)
+        floor = min(0.995, cosine(r, g32[name].flatten())) - 0.03
         ratio = (a.norm() / (r.norm() + 1e-30)).item()
-        if cos.item() < worst[0]:
-            worst = (cos.item(), name)
-        assert cos.item() >= 0.97, (name, cos.item(), ratio)
-        assert 0.9 <= ratio <= 1.1, (name, cos.item(), ratio)
-    print(f'{arch}: worst gradient cosine {worst}')
+        worst = min(worst, (cos, name))
+        assert cos >= floor, (name, cos, floor, ratio)
+        assert 0.9 <= ratio <= 1.1, (name, cos, ratio)
+        if name.startswith(('mask_decoder', 'depth_decoder')):
+            assert cos >= 0.99, (name, cos)
+    print(f'{arch}: worst gradient cosine vs storage-emulating oracle {worst}')
     # parameters that get no gradient in the reference get none here either (unused decoder BNs)
     for name, p in named.items():
-        if name not in ref_grads:
+        if name not in gq:
             assert p.grad is None, name
     # running statistics were updated like torch BatchNorm2d(momentum=0.1)
     new_sd = net.state_dict()
@@ -118,13 +134,16 @@ def test_train_step_reference_fixture_gradient_norms():
     targets = {k: v.cuda() for k, v in data.items() if k != 'image'}
     LossManager((0.1, 100.0), 0.25, side_outputs=False)(out, targets)['loss'].backward()
     named = dict(net.named_parameters())
+    # against the reference's own fp32 gradients: norms within 10 %; element-wise the bf16 forward flips ~1 % of
+    # the ReLU masks per layer, so deep encoder gradients agree in direction only to cos ~0.85
     for name, ref_norm in zip(gold['grad_names'], gold['grad_norms']):
         n = named[str(name)].grad.double().norm().item()
         assert abs(n - ref_norm) <= 0.1 * ref_norm + 1e-12, (str(name), n, ref_norm)
-        idx = torch.from_numpy(gold[f'grad/{name}/idx']).long()
-        ref = torch.from_numpy(gold[f'grad/{name}/val'])
-        got = named[str(name)].grad.flatten().cpu()[idx]
-        assert (got - ref).abs().max() <= 0.25 * ref.abs().max() + 1e-9, str(name)
+        if str(name).startswith(('mask_decoder', 'depth_decoder')):
+            idx = torch.from_numpy(gold[f'grad/{name}/idx']).long()
+            ref = torch.from_numpy(gold[f'grad/{name}/val'])
+            got = named[str(name)].grad.flatten().cpu()[idx]
+            assert (got - ref).abs().max() <= 0.1 * ref.abs().max() + 1e-9, str(name)
 
 
 def test_optimizer_step_through_reference_training_loop_surface():
