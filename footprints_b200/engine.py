@@ -67,6 +67,26 @@ class Engine:
         self._build_layers()
         self._weight_key = None
         self._bufs = {}
+        self.launches = 0           # kernels launched through the C ABI (bench.py reports them)
+        self.profile = None         # when a list: (kind, layer, flops, start_event, end_event) per conv launch
+        self._prof_open = None
+
+    # ------------------------------------------------------------------------------ instrumentation
+    def _prof(self, kind, L, m_pixels):
+        if self.profile is None:
+            return
+        k_real = 147 if L.stem else L.k * L.k * (L.cin0 + L.cin1)
+        flops = 2.0 * m_pixels * L.cout * k_real
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._prof_open = (kind, L.name, flops, e0, e1)
+
+    def _prof_end(self):
+        if self._prof_open is not None:
+            self._prof_open[4].record()
+            self.profile.append(self._prof_open)
+            self._prof_open = None
 
     # ------------------------------------------------------------------------------ plan
     def _add(self, layer):
@@ -190,9 +210,12 @@ class Engine:
         assert c0 == L.cin0 and d.c1 == L.cin1, (L.name, c0, d.c1, L.cin0, L.cin1)
         if src1 is not None:
             assert tuple(src1.shape[1:3]) == (hin, win), (L.name, src1.shape, hin, win)
+        self._prof('fwd', L, b * d.ho * d.wo)
         _lib.check(self.lib.fp_conv_fwd(ctypes.byref(d), _ptr(src0), _ptr(src1), _ptr(L.w_packed),
                                         _ptr(L.scale if scale is None else scale),
                                         _ptr(L.shift if shift is None else shift), _ptr(residual), _ptr(out), stream))
+        self._prof_end()
+        self.launches += 1
 
     # ------------------------------------------------------------------------------ forward (inference)
     @torch.no_grad()

@@ -38,6 +38,13 @@ class TrainEngine(Engine):
         self._red_ws = None
         self._wg_ws = None
         self._loss_ws = None
+        self.grad_views = None      # optional {parameter: fp32 view} — gradients are written there (Trainer's flat buffer)
+
+    def _gout(self, param, shape=None):
+        """fp32 destination of a parameter gradient: the Trainer's flat-buffer view when present."""
+        if self.grad_views is not None and param in self.grad_views:
+            return self.grad_views[param]
+        return torch.empty(param.shape if shape is None else shape, dtype=torch.float32, device=param.device)
 
     # ------------------------------------------------------------------------------ helpers
     def _dev(self):
@@ -224,14 +231,24 @@ class TrainEngine(Engine):
         need = self.lib.fp_conv_wgrad_workspace_bytes(ctypes.byref(d))
         if self._wg_ws is None or self._wg_ws.numel() * 4 < need:
             self._wg_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=dz.device)
-        dw = torch.empty(L.weight.shape, dtype=torch.float32, device=dz.device)
+        dw = self._gout(L.weight)
+        self._prof('wgrad', L, b * ho * wo)
         _lib.check(self.lib.fp_conv_wgrad(ctypes.byref(d), _ptr(src0), _ptr(src1), _ptr(dz), ld, self.gfmt,
                                           1 if L.stem else 0, 0, _ptr(dw), _ptr(self._wg_ws), stream))
+        self._prof_end()
+        self.launches += 2
         grads[L.weight] = dw
         if L.bias is not None:
-            db = torch.empty(ld, dtype=torch.float32, device=dz.device)
-            _lib.check(self.lib.fp_bias_grad(_ptr(dz), b * ho * wo, ld, self.gfmt, _ptr(db), _ptr(self._reduce_ws()), stream))
-            grads[L.bias] = db[:L.cout] if ld != L.cout else db
+            if ld == L.cout:
+                db = self._gout(L.bias)
+                _lib.check(self.lib.fp_bias_grad(_ptr(dz), b * ho * wo, ld, self.gfmt, _ptr(db), _ptr(self._reduce_ws()), stream))
+            else:       # heads: dZ rows are padded to 8 channels, the bias has 2
+                tmp = torch.empty(ld, dtype=torch.float32, device=dz.device)
+                _lib.check(self.lib.fp_bias_grad(_ptr(dz), b * ho * wo, ld, self.gfmt, _ptr(tmp), _ptr(self._reduce_ws()), stream))
+                db = self._gout(L.bias)
+                db.copy_(tmp[:L.cout])
+            self.launches += 2
+            grads[L.bias] = db
 
     def _dgrad_full(self, L, dz, stream):
         """Gradient of the reflection-padded virtual input: zero-padded full correlation of dZ with the rotated
@@ -247,7 +264,10 @@ class TrainEngine(Engine):
         d.cout, d.kpad, d.npad, d.bn = cin, L.d_kpad, L.d_npad, L.d_bn
         d.act, d.dtype, d.out_f32, d.out_ld, d.res_ld, d.b_via_tma = FP_ACT_NONE, self.gfmt, 0, cin, 0, 1
         assert ld == L.cpad_out, (L.name, ld, L.cpad_out)
+        self._prof('dgrad', L, b * ho * wo)
         _lib.check(self.lib.fp_conv_fwd(ctypes.byref(d), _ptr(dz), None, _ptr(L.w_flip), None, None, None, _ptr(out), stream))
+        self._prof_end()
+        self.launches += 1
         return out
 
     def _dgrad_plain(self, L, dz, out_hw, residual, stream):
@@ -267,12 +287,16 @@ class TrainEngine(Engine):
         d.cout, d.kpad, d.npad, d.bn = cin, L.d_kpad, L.d_npad, L.d_bn
         d.act, d.dtype, d.out_f32, d.out_ld, d.b_via_tma = FP_ACT_NONE, self.gfmt, 0, cin, 1
         d.res_ld = cin if residual is not None else 0
+        self._prof('dgrad', L, b * ho * wo)
         _lib.check(self.lib.fp_conv_fwd(ctypes.byref(d), _ptr(dz), None, _ptr(L.w_flip), None, None, _ptr(residual),
                                         _ptr(out), stream))
+        self._prof_end()
+        self.launches += 1
         return out
 
     def _fold(self, dvp, hv, wv, coff, c, up, dst, accumulate, y_act, act, stream):
         b = dvp.shape[0]
+        self.launches += 1
         _lib.check(self.lib.fp_fold_bwd(_ptr(dvp), b, hv, wv, dvp.shape[3], coff, c, 1 if up else 0, 1 if accumulate else 0,
                                         _ptr(y_act), act, self.fmt, self.gfmt, _ptr(dst), stream))
 
@@ -282,11 +306,12 @@ class TrainEngine(Engine):
         b, ho, wo, c = z.shape
         dz = torch.empty(z.shape, dtype=self.gdtype, device=z.device)
         g = torch.empty(z.shape, dtype=self.gdtype, device=z.device) if want_g else None
-        dgamma = torch.empty(c, dtype=torch.float32, device=z.device)
-        dbeta = torch.empty(c, dtype=torch.float32, device=z.device)
+        dgamma = self._gout(L.bn.weight)
+        dbeta = self._gout(L.bn.bias)
         _lib.check(self.lib.fp_bn_bwd(_ptr(dy), _ptr(y), _ptr(z), _ptr(L.bn.weight.detach()), _ptr(st['mean']),
                                       _ptr(st['invstd']), 1 if relu else 0, b * ho * wo, c, self.fmt, self.gfmt, _ptr(dz),
                                       _ptr(g), _ptr(dgamma), _ptr(dbeta), _ptr(self._reduce_ws()), stream))
+        self.launches += 3
         grads[L.bn.weight] = dgamma
         grads[L.bn.bias] = dbeta
         return dz, g
