@@ -51,6 +51,7 @@ PROTOTYPES = {
     'fp_maxpool3x3s2_bwd': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_conv_wgrad_workspace_bytes': (ctypes.c_longlong, [ctypes.POINTER(FpConvDesc)]),
     'fp_conv_wgrad': (ctypes.c_int, [ctypes.POINTER(FpConvDesc), _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    'fp_debug_read_trace': (ctypes.c_int, [_vp]),
     'fp_adam_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
 }
 

@@ -36,6 +36,9 @@ constexpr int NUM_THREADS = (EPI_FIRST_WARP + NUM_EPI_WARPS) * 32;   // 544
 constexpr int ROWS_PER_THREAD = BM / (NUM_PRODUCER_THREADS / 8);     // 4
 constexpr int KTAB_ENTRIES = 1024;   // one entry per 16-byte K chunk: kpad <= 8192
 
+// perf triage (FP_DEBUG_FLAGS & 16): CTA 0 records clock64() stamps: [role][event idx]
+__device__ long long g_trace[3][2048];
+
 template <int BN>
 struct IgemmCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
@@ -55,21 +58,41 @@ struct IgemmParams {
   int N;
   int num_kb, kpad, m_tiles, n_tiles, total_tiles;
   int act, fmt, w_fmt, out_f32, out_ld, res_ld, b_via_tma;
+  int a_mode;                // 0: cp.async gather (any channel count), 1: TMA tile::gather4 (C0, C1 multiples of 64)
+  int rows0, rows1;          // pixel counts of the two sources (first out-of-range TMA row index)
   int debug;                 // FP_DEBUG_FLAGS (perf triage only): 1 skip A gather, 2 skip MMA, 4 skip epilogue math, 8 skip B load
 };
 
 
-// ELU(alpha=1) negative branch: expm1 via a short Taylor series near 0 and ex2.approx elsewhere
-// (abs error < 1e-7, far below the 16-bit output rounding).
-__device__ __forceinline__ float fast_expm1_neg(float x) {
-  const float poly = x * (1.f + x * (0.5f + x * (0.16666667f + x * 0.041666668f)));
-  return x > -0.125f ? poly : __expf(x) - 1.f;
+// exp(x) by ex2.approx (one FMUL + one MUFU); |rel err| ~ 2^-22, far below the 16-bit output rounding
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
 }
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == FP_ACT_RELU) return fmaxf(x, 0.f);
-  if (act == FP_ACT_ELU) return x > 0.f ? x : fast_expm1_neg(x);
-  if (act == FP_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+// Branch-free activations with the kind as a compile-time constant: the epilogue is on the critical path of the
+// small-N layers (one accumulator drain per 128x64 tile), so no per-element jump table / divergent branches.
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if (ACT == FP_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == FP_ACT_ELU) return x > 0.f ? x : fast_exp(x) - 1.f;          // select, both sides evaluated
+  if (ACT == FP_ACT_SIGMOID) return __frcp_rn(1.f + fast_exp(-x));
   return x;
+}
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2t(float a, float b) {
+  if (FMT == FP_BF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <int FMT>
+__device__ __forceinline__ float2 unpack2t(uint32_t u) {
+  if (FMT == FP_BF16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
@@ -85,9 +108,79 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
+// Drain `ncols_total` accumulator columns of this thread's row (TMEM lane) starting at column `col0`:
+// y = act(acc*scale + shift (+ residual)) -> 16-bit or fp32 NHWC row.  ACT and FMT are compile-time.
+template <int ACT, int FMT>
+__device__ __forceinline__ void epilogue_cols(const IgemmParams& p, uint32_t tbase, int col0, int ncols_total, int n_base,
+                                              int m, bool row_ok, const float* s_scale, const float* s_shift) {
+  constexpr int CW = 16;
+#pragma unroll 1
+  for (int j = col0; j < col0 + ncols_total; j += CW) {
+    uint32_t v[CW];
+    tmem_ld_32x32b_x16(tbase + j, v);
+    tmem_ld_wait();
+    const int n0 = n_base + j;
+    if (row_ok && n0 < p.N) {
+      float f[CW];
+#pragma unroll
+      for (int x = 0; x < CW; ++x) f[x] = __uint_as_float(v[x]) * s_scale[j + x] + s_shift[j + x];
+      const int ncols = min(CW, p.N - n0);
+      if (p.residual != nullptr) {
+        const uint8_t* rp = p.residual + (static_cast<size_t>(m) * p.res_ld + n0) * 2;
+        if (ncols == CW) {
+#pragma unroll
+          for (int x = 0; x < CW / 8; ++x) {
+            const uint4 r = *reinterpret_cast<const uint4*>(rp + x * 16);
+            float2 t;
+            t = unpack2t<FMT>(r.x); f[x * 8 + 0] += t.x; f[x * 8 + 1] += t.y;
+            t = unpack2t<FMT>(r.y); f[x * 8 + 2] += t.x; f[x * 8 + 3] += t.y;
+            t = unpack2t<FMT>(r.z); f[x * 8 + 4] += t.x; f[x * 8 + 5] += t.y;
+            t = unpack2t<FMT>(r.w); f[x * 8 + 6] += t.x; f[x * 8 + 7] += t.y;
+          }
+        } else {
+#pragma unroll
+          for (int x = 0; x < CW; ++x)
+            if (x < ncols) f[x] += unpack2t<FMT>(*reinterpret_cast<const uint16_t*>(rp + x * 2)).x;
+        }
+      }
+#pragma unroll
+      for (int x = 0; x < CW; ++x) f[x] = apply_act<ACT>(f[x]);
+      if (p.out_f32) {
+        float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + n0;
+        if (ncols == CW && (p.out_ld & 3) == 0) {
+#pragma unroll
+          for (int x = 0; x < CW / 4; ++x)
+            *reinterpret_cast<float4*>(op + 4 * x) = make_float4(f[4 * x], f[4 * x + 1], f[4 * x + 2], f[4 * x + 3]);
+        } else {
+#pragma unroll
+          for (int x = 0; x < CW; ++x) if (x < ncols) op[x] = f[x];
+        }
+      } else {
+        uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (static_cast<size_t>(m) * p.out_ld + n0) * 2;
+        if (ncols == CW && (p.out_ld & 7) == 0) {
+#pragma unroll
+          for (int x = 0; x < CW / 8; ++x) {
+            uint4 o;
+            o.x = pack2t<FMT>(f[8 * x], f[8 * x + 1]);
+            o.y = pack2t<FMT>(f[8 * x + 2], f[8 * x + 3]);
+            o.z = pack2t<FMT>(f[8 * x + 4], f[8 * x + 5]);
+            o.w = pack2t<FMT>(f[8 * x + 6], f[8 * x + 7]);
+            *reinterpret_cast<uint4*>(op + 16 * x) = o;
+          }
+        } else {
+#pragma unroll
+          for (int x = 0; x < CW; ++x)
+            if (x < ncols) *reinterpret_cast<uint16_t*>(op + 2 * x) = static_cast<uint16_t>(pack2t<FMT>(f[x], 0.f) & 0xFFFF);
+        }
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__ CUtensorMap tmap_w) {
+conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__ CUtensorMap tmap_w,
+                  const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1) {
   using Cfg = IgemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int B_STAGE_BYTES = Cfg::B_STAGE_BYTES;
@@ -113,7 +206,9 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], NUM_PRODUCER_THREADS + (p.b_via_tma ? 1 : 0));   // one async arrive per producer thread
+      // cp.async gather: one async arrive per producer thread (+1 for the weight TMA's expect_tx);
+      // TMA gather: a single expect_tx arrive, everything else is transaction bytes
+      mbar_init(&full_bar[s], p.a_mode == 1 ? 1 : NUM_PRODUCER_THREADS + (p.b_via_tma ? 1 : 0));
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -122,6 +217,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
     }
     fence_barrier_init();
     if (p.b_via_tma) tma_prefetch_desc(&tmap_w);
+    if (p.a_mode == 1) { tma_prefetch_desc(&tmap_a0); if (p.g.C1 > 0) tma_prefetch_desc(&tmap_a1); }
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
   for (int j = tid; j < p.num_kb * 8; j += NUM_THREADS) s_ktab[j] = make_ktab_entry(p.g, j, p.num_kb * 8);
@@ -130,8 +226,51 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp < NUM_PRODUCER_WARPS) {
-    // =============================== PRODUCERS ===============================
+  if (p.a_mode == 1 && warp < NUM_PRODUCER_WARPS) {
+    // =============================== PRODUCERS (TMA tile::gather4) ===============================
+    // Warps 0-3: warp w owns K blocks kb = w (mod 4); lane L fetches rows 4L..4L+3 of the tile with one gather4
+    // (four source pixels x 64 channels = 4 x 128 B, swizzled by the TMA unit).  Completion is pure transaction
+    // bytes on the stage's mbarrier, so nobody waits for loads and the MMA warp sees one arrival per stage.
+    if (warp < 4) {
+      uint32_t ti = 0;
+      uint32_t it_base = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti, it_base += p.num_kb) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        uint4* info_buf = s_rowinfo + (ti & 1) * BM;
+        {
+          const int m = m_tile * BM + tid;      // tid < 128 here
+          uint4 ri = make_uint4(0u, 0xFFFFFFFFu, 0u, 0xFFFFFFFFu);
+          if (m < p.g.M) ri = make_row_info_for_pixel(p.g, m, true);
+          info_buf[tid] = ri;
+        }
+        named_bar_sync(2, 128);
+        uint4 info[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) info[i] = info_buf[4 * lane + i];
+        for (int kb = warp; kb < p.num_kb; kb += 4) {
+          const uint32_t it = it_base + kb;
+          const int s = it % STAGES;
+          if (lane == 0) {
+            mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1, 1);
+            if ((p.debug & 16) && blockIdx.x == 0 && it < 2048) g_trace[0][it] = clock64();
+            mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + (p.b_via_tma ? B_STAGE_BYTES : 0));
+            if (p.b_via_tma)
+              tma_load_2d(smem_u32(b_smem) + s * B_STAGE_BYTES, &tmap_w, &full_bar[s], kb * BK, n_tile * BN);
+          }
+          __syncwarp();
+          const KDecode kd = decode_ktab(p.g, s_ktab[kb * 8]);
+          const int pitch = kd.second ? p.g.Win : p.g.W0;
+          const int oob = kd.second ? p.rows1 : p.rows0;
+          const int r0 = gather_row_index(kd, info[0], pitch, oob), r1 = gather_row_index(kd, info[1], pitch, oob);
+          const int r2 = gather_row_index(kd, info[2], pitch, oob), r3 = gather_row_index(kd, info[3], pitch, oob);
+          tma_gather4_2d(smem_u32(a_smem) + s * A_STAGE_BYTES + lane * 512, kd.second ? &tmap_a1 : &tmap_a0, &full_bar[s],
+                         static_cast<int>(kd.cc), r0, r1, r2, r3);
+        }
+      }
+    }
+  } else if (warp < NUM_PRODUCER_WARPS) {
+    // =============================== PRODUCERS (cp.async gather) ===============================
     const int c = tid & 7;    // 16-byte chunk (8 channels) within the 128-byte K row
     const int r0 = tid >> 3;  // rows r0 + 32*i, i = 0..3
     const uint32_t swz = static_cast<uint32_t>(r0 * 128 + ((c ^ (r0 & 7)) << 4));
@@ -158,6 +297,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
         const uint32_t ph = (it / STAGES) & 1;
         if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1, 1);
         __syncwarp();
+        if ((p.debug & 16) && blockIdx.x == 0 && tid == 0 && it < 2048) g_trace[0][it] = clock64();
         if (p.b_via_tma) {
           if (tid == 0) {
             if (p.debug & 8) mbar_arrive(&full_bar[s]);
@@ -202,6 +342,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&full_bar[s], (it / STAGES) & 1, 3);
+          if ((p.debug & 16) && blockIdx.x == 0 && it < 2048) g_trace[1][it] = clock64();
           tcgen05_fence_after();
           const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(a_smem) + s * A_STAGE_BYTES, 16, 1024);
           const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(b_smem) + s * B_STAGE_BYTES, 16, 1024);
@@ -224,7 +365,6 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
     const int half = (warp - EPI_FIRST_WARP) >> 2;
     const int row = q * 32 + lane;
     const int e = tid - EPI_FIRST_WARP * 32;
-    constexpr int CW = 16;
     constexpr int COLS_PER_HALF = (BN >= 32) ? BN / 2 : BN;
     const int col_begin = (BN >= 32) ? half * COLS_PER_HALF : 0;
     const bool active = (BN >= 32) || (half == 0);
@@ -241,75 +381,34 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
       }
       named_bar_sync(1, NUM_EPI_THREADS);
       mbar_wait<128>(&tmem_full_bar[acc], (ti >> 1) & 1, 4);
+      if ((p.debug & 16) && blockIdx.x == 0 && e == 0 && ti < 1024) g_trace[2][2 * ti] = clock64();
       tcgen05_fence_after();
       const int m = m_tile * BM + row;
       const bool m_ok = m < p.g.M;
       if (active) {
-#pragma unroll 1
-        for (int j = col_begin; j < col_begin + COLS_PER_HALF; j += CW) {
-          uint32_t v[CW];
-          const uint32_t taddr = tmem_base + acc * BN + j + (static_cast<uint32_t>(q * 32) << 16);
-          tmem_ld_32x32b_x16(taddr, v);
-          tmem_ld_wait();
-          const int n0 = n_tile * BN + j;
-          if (m_ok && n0 < p.N && !(p.debug & 4)) {
-            float f[CW];
-#pragma unroll
-            for (int x = 0; x < CW; ++x) f[x] = __uint_as_float(v[x]) * s_scale[j + x] + s_shift[j + x];
-            const int ncols = min(CW, p.N - n0);
-            if (p.residual != nullptr) {
-              const uint8_t* rp = p.residual + (static_cast<size_t>(m) * p.res_ld + n0) * 2;
-              if (ncols == CW) {
-#pragma unroll
-                for (int x = 0; x < CW / 8; ++x) {
-                  const uint4 r = *reinterpret_cast<const uint4*>(rp + x * 16);
-                  float2 t;
-                  t = unpack2(r.x, p.fmt); f[x * 8 + 0] += t.x; f[x * 8 + 1] += t.y;
-                  t = unpack2(r.y, p.fmt); f[x * 8 + 2] += t.x; f[x * 8 + 3] += t.y;
-                  t = unpack2(r.z, p.fmt); f[x * 8 + 4] += t.x; f[x * 8 + 5] += t.y;
-                  t = unpack2(r.w, p.fmt); f[x * 8 + 6] += t.x; f[x * 8 + 7] += t.y;
-                }
-              } else {
-#pragma unroll
-                for (int x = 0; x < CW; ++x)
-                  if (x < ncols) f[x] += unpack2(*reinterpret_cast<const uint16_t*>(rp + x * 2), p.fmt).x;
-              }
-            }
-#pragma unroll
-            for (int x = 0; x < CW; ++x) f[x] = apply_act(f[x], p.act);
-            if (p.out_f32) {
-              float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + n0;
-              if (ncols == CW && (p.out_ld & 3) == 0) {
-#pragma unroll
-                for (int x = 0; x < CW / 4; ++x)
-                  *reinterpret_cast<float4*>(op + 4 * x) = make_float4(f[4 * x], f[4 * x + 1], f[4 * x + 2], f[4 * x + 3]);
-              } else {
-#pragma unroll
-                for (int x = 0; x < CW; ++x) if (x < ncols) op[x] = f[x];
-              }
-            } else {
-              uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (static_cast<size_t>(m) * p.out_ld + n0) * 2;
-              if (ncols == CW && (p.out_ld & 7) == 0) {
-#pragma unroll
-                for (int x = 0; x < CW / 8; ++x) {
-                  uint4 o;
-                  o.x = pack2(f[8 * x], f[8 * x + 1], p.fmt);
-                  o.y = pack2(f[8 * x + 2], f[8 * x + 3], p.fmt);
-                  o.z = pack2(f[8 * x + 4], f[8 * x + 5], p.fmt);
-                  o.w = pack2(f[8 * x + 6], f[8 * x + 7], p.fmt);
-                  *reinterpret_cast<uint4*>(op + 16 * x) = o;
-                }
-              } else {
-#pragma unroll
-                for (int x = 0; x < CW; ++x)
-                  if (x < ncols) *reinterpret_cast<uint16_t*>(op + 2 * x) = static_cast<uint16_t>(pack2(f[x], 0.f, p.fmt) & 0xFFFF);
-              }
-            }
+        const uint32_t tbase = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+        const bool skip = (p.debug & 4) != 0;
+#define FP_EPI(A, F) epilogue_cols<A, F>(p, tbase, col_begin, COLS_PER_HALF, n_tile * BN, m, m_ok && !skip, s_scale, s_shift)
+        if (p.fmt == FP_BF16) {
+          switch (p.act) {
+            case FP_ACT_RELU: FP_EPI(FP_ACT_RELU, FP_BF16); break;
+            case FP_ACT_ELU: FP_EPI(FP_ACT_ELU, FP_BF16); break;
+            case FP_ACT_SIGMOID: FP_EPI(FP_ACT_SIGMOID, FP_BF16); break;
+            default: FP_EPI(FP_ACT_NONE, FP_BF16); break;
+          }
+        } else {
+          switch (p.act) {
+            case FP_ACT_RELU: FP_EPI(FP_ACT_RELU, FP_F16); break;
+            case FP_ACT_ELU: FP_EPI(FP_ACT_ELU, FP_F16); break;
+            case FP_ACT_SIGMOID: FP_EPI(FP_ACT_SIGMOID, FP_F16); break;
+            default: FP_EPI(FP_ACT_NONE, FP_F16); break;
           }
         }
+#undef FP_EPI
       }
       tcgen05_fence_before();
       __syncwarp();
+      if ((p.debug & 16) && blockIdx.x == 0 && e == 0 && ti < 1024) g_trace[2][2 * ti + 1] = clock64();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
@@ -326,7 +425,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
 // host side
 // --------------------------------------------------------------------------------------------------
 template <int BN>
-static int launch_igemm(const IgemmParams& p, const CUtensorMap& tmap, cudaStream_t stream) {
+static int launch_igemm(const IgemmParams& p, const CUtensorMap& tmap, const CUtensorMap& tmap_a0,
+                        const CUtensorMap& tmap_a1, cudaStream_t stream) {
   using Cfg = IgemmCfg<BN>;
   static bool attr_set = false;
   auto kern = conv_igemm_kernel<BN>;
@@ -336,7 +436,7 @@ static int launch_igemm(const IgemmParams& p, const CUtensorMap& tmap, cudaStrea
     attr_set = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p, tmap);
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p, tmap, tmap_a0, tmap_a1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "conv_igemm launch (BN=%d): %s", BN, cudaGetErrorString(e));
   return FP_OK;
@@ -411,13 +511,36 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
                             static_cast<uint32_t>(d->bn));
     if (rc != FP_OK) return rc;
   }
+  // A operand by TMA tile::gather4 when every 128-byte K row is 64 channels of one tap of one source
+  CUtensorMap tmap_a0, tmap_a1;
+  memset(&tmap_a0, 0, sizeof(tmap_a0));
+  memset(&tmap_a1, 0, sizeof(tmap_a1));
+  const char* amode_env = getenv("FP_A_MODE");
+  const bool gather_ok = (d->c0 % 64 == 0) && (d->c1 % 64 == 0) && d->b_via_tma;
+  p.a_mode = (gather_ok && !(amode_env && atoi(amode_env) == 0)) ? 1 : 0;
+  if (p.a_mode == 1) {
+    p.rows0 = d->batch * d->h0 * d->w0;
+    p.rows1 = d->batch * p.g.Hin * p.g.Win;
+    rc = make_tmap_2d_sw128(&tmap_a0, src0, static_cast<uint64_t>(d->c0), static_cast<uint64_t>(p.rows0), 64u, 1u);
+    if (rc != FP_OK) return rc;
+    if (d->c1 > 0) {
+      rc = make_tmap_2d_sw128(&tmap_a1, src1, static_cast<uint64_t>(d->c1), static_cast<uint64_t>(p.rows1), 64u, 1u);
+      if (rc != FP_OK) return rc;
+    }
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (d->bn) {
-    case 16: return launch_igemm<16>(p, tmap, st);
-    case 32: return launch_igemm<32>(p, tmap, st);
-    case 64: return launch_igemm<64>(p, tmap, st);
-    case 128: return launch_igemm<128>(p, tmap, st);
-    case 256: return launch_igemm<256>(p, tmap, st);
+    case 16: return launch_igemm<16>(p, tmap, tmap_a0, tmap_a1, st);
+    case 32: return launch_igemm<32>(p, tmap, tmap_a0, tmap_a1, st);
+    case 64: return launch_igemm<64>(p, tmap, tmap_a0, tmap_a1, st);
+    case 128: return launch_igemm<128>(p, tmap, tmap_a0, tmap_a1, st);
+    case 256: return launch_igemm<256>(p, tmap, tmap_a0, tmap_a1, st);
     default: return set_error(FP_ERR_ARG, "fp_conv_fwd: bn=%d not in {16,32,64,128,256}", d->bn);
   }
+}
+
+// perf triage helper: copies CTA 0's clock stamps (FP_DEBUG_FLAGS & 16) to the host; out[3][2048]
+extern "C" int fp_debug_read_trace(long long* out) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, fp::g_trace, sizeof(long long) * 3 * 2048);
+  return e == cudaSuccess ? FP_OK : fp::set_error(FP_ERR_CUDA, "fp_debug_read_trace: %s", cudaGetErrorString(e));
 }

@@ -111,6 +111,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+// Blackwell tile::gather4: four arbitrary rows (r0..r3) x box-columns starting at column `col` of a 2-D tensor
+// land as four consecutive (swizzled) rows in shared memory; out-of-range rows are filled with zeros.
+__device__ __forceinline__ void tma_gather4_2d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int col, int r0,
+                                               int r1, int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3),
+        "r"(smem_u32(bar))
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, UMMA, commit, TMEM loads
 // ----------------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ __device__ __forceinline__ void make_row_info(int n, int y0, int x0, int Hv, int
                                               int KH, int KW, int reflect, uint32_t& base, uint32_t& code) {
   const int sh = up ? 1 : 0;
   const int refy = max(y0, 0) >> sh, refx = max(x0, 0) >> sh;
-  base = static_cast<uint32_t>(((n * Hs + refy) * Ws + refx) * Cs);
+  base = static_cast<uint32_t>(((n * Hs + refy) * Ws + refx) * Cs);   // Cs = 1: pixel index (TMA gather rows)
   uint32_t cd = 0;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
@@ -50,16 +50,18 @@ __device__ __forceinline__ void make_row_info(int n, int y0, int x0, int Hv, int
   code = cd;
 }
 
-// {base0, code0, base1, code1} for output pixel m (caller guarantees m < g.M)
-__device__ __forceinline__ uint4 make_row_info_for_pixel(const GatherGeom& g, int m) {
+// {base0, code0, base1, code1} for output pixel m (caller guarantees m < g.M); pixel_units: bases are pixel
+// indices (row coordinates of the TMA gather tensor maps) instead of element offsets
+__device__ __forceinline__ uint4 make_row_info_for_pixel(const GatherGeom& g, int m, bool pixel_units = false) {
   const int n = m / g.HoWo;
   const int rem = m - n * g.HoWo;
   const int oy = rem / g.Wo;
   const int ox = rem - oy * g.Wo;
   const int y0 = oy * g.stride - g.pad_t, x0 = ox * g.stride - g.pad_l;
   uint4 ri = make_uint4(0u, 0xFFFFFFFFu, 0u, 0xFFFFFFFFu);
-  make_row_info(n, y0, x0, g.Hin, g.Win, g.up0, g.H0, g.W0, g.C0, g.KH, g.KW, g.pad_mode, ri.x, ri.y);
-  if (g.C1 > 0) make_row_info(n, y0, x0, g.Hin, g.Win, 0, g.Hin, g.Win, g.C1, g.KH, g.KW, g.pad_mode, ri.z, ri.w);
+  make_row_info(n, y0, x0, g.Hin, g.Win, g.up0, g.H0, g.W0, pixel_units ? 1 : g.C0, g.KH, g.KW, g.pad_mode, ri.x, ri.y);
+  if (g.C1 > 0)
+    make_row_info(n, y0, x0, g.Hin, g.Win, 0, g.Hin, g.Win, pixel_units ? 1 : g.C1, g.KH, g.KW, g.pad_mode, ri.z, ri.w);
   return ri;
 }
 
@@ -102,6 +104,16 @@ __device__ __forceinline__ uint32_t gather_offset(const KDecode& k, const uint4&
   const uint32_t dy = (code >> k.shy) & 15u, dx = (code >> k.shx) & 15u;
   ok = ((dy | dx | k.padmask) & 8u) == 0u;
   return ok ? base + dy * k.rstride + dx * k.pstride + k.cc : 0u;
+}
+
+// TMA-gather flavour: source row (pixel) index of the chunk's tap for the row described by `ri`, or `oob_row`
+// (any index >= the tensor's row count: the TMA fills zeros) when the tap reads padding
+__device__ __forceinline__ int gather_row_index(const KDecode& k, const uint4& ri, int row_pitch_pixels, int oob_row) {
+  const uint32_t code = k.second ? ri.w : ri.y;
+  const uint32_t base = k.second ? ri.z : ri.x;
+  const uint32_t dy = (code >> k.shy) & 15u, dx = (code >> k.shx) & 15u;
+  const bool ok = ((dy | dx | k.padmask) & 8u) == 0u;
+  return ok ? static_cast<int>(base + dy * row_pitch_pixels + dx) : oob_row;
 }
 
 // host: validate an FpConvDesc's gather part and fill the geometry

@@ -170,6 +170,16 @@ static int run_case(const Case& c, bool time_it) {
       rc = 1;
     }
   }
+  if (getenv("FP_TRACE")) {
+    static long long tr[3][2048];
+    FPCK(fp_conv_fwd(&d, ds0, n1 ? ds1 : nullptr, dwp, sc, dshift, rs, dout, nullptr));
+    CK(cudaDeviceSynchronize());
+    FPCK(fp_debug_read_trace(&tr[0][0]));
+    const long long t0 = tr[0][0];
+    printf("  trace (cycles rel. to first producer stamp): kb: producer_free  mma_full | tile: epi_start epi_end\n");
+    for (int i = 0; i < 64; ++i) printf("   it %3d  P %8lld  M %8lld\n", i, tr[0][i] - t0, tr[1][i] - t0);
+    for (int i = 0; i < 8; ++i) printf("   tile %d  E %8lld .. %8lld\n", i, tr[2][2 * i] - t0, tr[2][2 * i + 1] - t0);
+  }
   if (time_it) {
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int i = 0; i < 3; ++i) FPCK(fp_conv_fwd(&d, ds0, n1 ? ds1 : nullptr, dwp, sc, dshift, rs, dout, nullptr));

