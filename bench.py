@@ -259,10 +259,12 @@ def main():
 
     # ---- roofline of the dominant kernel class (tcgen05 implicit-GEMM conv: forward + data-gradient launches)
     roofline = None
+    # every rank runs the instrumented step (it contains the gradient all-reduce); only rank 0 records events
     if rank == 0:
         eng.profile = []
-        step_resident()
-        torch.cuda.synchronize()
+    step_resident()
+    torch.cuda.synchronize()
+    if rank == 0:
         prof, eng.profile = eng.profile, None
         agg = {}
         for kind, name, flops, a, b in prof:

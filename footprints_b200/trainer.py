@@ -15,6 +15,7 @@ import ctypes
 import torch
 
 from . import _lib
+from .dp import GradSync
 from .engine import SCALES
 from .losses import fused_loss
 
@@ -40,8 +41,8 @@ class Trainer:
         self.eng = net.train_engine()
         self.lr, self.betas, self.eps = lr, betas, eps
         self.depth_range, self.prior = depth_range, footprint_prior
-        self.pg = process_group
-        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.sync = GradSync(process_group)
+        self.pg, self.world = self.sync.pg, self.sync.world
         self.params = trainable_parameters(net)
         dev = self.params[0].device
         # 16-byte aligned slots in one flat buffer
@@ -66,10 +67,7 @@ class Trainer:
 
     def broadcast_parameters(self):
         """Make every rank start from rank 0's weights (and BatchNorm buffers)."""
-        if self.world > 1:
-            torch.distributed.broadcast(self.flat, 0, group=self.pg)
-            for b in self.net.buffers():
-                torch.distributed.broadcast(b, 0, group=self.pg)
+        self.sync.broadcast_([self.flat] + list(self.net.buffers()))
 
     def step(self, image, targets):
         """One training step on this rank's shard.  Returns the 21 losses as a device tensor (no host sync)."""
@@ -77,12 +75,11 @@ class Trainer:
         losses21, grads = fused_loss([outs[k] for k in SCALES], targets, self.depth_range, self.prior, True)
         self.eng.launches += 2
         self.eng.backward(dict(zip(SCALES, grads)))
-        if self.world > 1:
-            torch.distributed.all_reduce(self.grad, group=self.pg)       # sum over ranks; Adam applies 1/world
+        self.sync.all_reduce_(self.grad)                                  # sum over ranks; Adam applies 1/world
         self.step_count += 1
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(self.lib.fp_adam_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                                          self.exp_avg_sq.data_ptr(), self.flat.numel(), self.lr, self.betas[0],
-                                         self.betas[1], self.eps, self.step_count, 1.0 / self.world, stream))
+                                         self.betas[1], self.eps, self.step_count, self.sync.grad_scale, stream))
         self.eng.launches += 1
         return losses21
