@@ -38,6 +38,10 @@ PROTOTYPES = {
     'fp_stem_prep': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_maxpool3x3s2': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_heads_to_nchw': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    'fp_head_conv_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    'fp_head_conv_dgrad': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp]),
+    'fp_head_conv_wgrad_workspace_floats': (ctypes.c_longlong, [_i32]),
+    'fp_head_conv_wgrad': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     'fp_reduce_workspace_floats': (ctypes.c_int, [_i32]),
     'fp_bn_stats': (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
     'fp_bn_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),

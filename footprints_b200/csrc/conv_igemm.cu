@@ -517,7 +517,7 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
   memset(&tmap_a1, 0, sizeof(tmap_a1));
   const char* amode_env = getenv("FP_A_MODE");
   const bool gather_ok = (d->c0 % 64 == 0) && (d->c1 % 64 == 0) && d->b_via_tma;
-  p.a_mode = (gather_ok && !(amode_env && atoi(amode_env) == 0)) ? 1 : 0;
+  p.a_mode = (gather_ok && amode_env && atoi(amode_env) == 1) ? 1 : 0;   // opt-in (FP_A_MODE=1): measured no faster than cp.async
   if (p.a_mode == 1) {
     p.rows0 = d->batch * d->h0 * d->w0;
     p.rows1 = d->batch * p.g.Hin * p.g.Win;

@@ -207,24 +207,31 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__
 // dW_oihw[co][ci][ky][kx] (+)= sum over splits of partial[split][co][(ky*kw+kx)*cin + ci]; stem = 1 inverts the
 // space-to-depth packing of fp_pack_stem_weight.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int co_rows, int kpad, int cout,
-                                    int cin, int kh, int kw, int stem, int accumulate, float* __restrict__ dw) {
+                                    int cin, int cpad, int kh, int kw, int stem, int accumulate, float* __restrict__ dw) {
+  // one thread per (co, k) of the packed layout: consecutive threads read consecutive k (coalesced) in every split
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(cout) * cin * kh * kw;
-  if (idx >= total) return;
-  const int kx = static_cast<int>(idx % kw);
-  const int ky = static_cast<int>((idx / kw) % kh);
-  const int ci = static_cast<int>((idx / (kw * kh)) % cin);
-  const int co = static_cast<int>(idx / (static_cast<long long>(kw) * kh * cin));
-  int k;
+  if (idx >= static_cast<long long>(cout) * kpad) return;
+  const int k = static_cast<int>(idx % kpad);
+  const int co = static_cast<int>(idx / kpad);
+  int ci, ky, kx;
   if (stem) {
-    const int bh = (ky + 1) >> 1, dy = (ky + 1) & 1, bw = (kx + 1) >> 1, dx = (kx + 1) & 1;
-    k = (bh * 4 + bw) * 16 + (dy * 2 + dx) * 4 + ci;
+    const int tap = k >> 4, ch = k & 15;
+    const int bh = tap >> 2, bw = tap & 3, sub = ch >> 2;
+    ci = ch & 3;
+    ky = 2 * bh + (sub >> 1) - 1;
+    kx = 2 * bw + (sub & 1) - 1;
+    if (ci >= 3 || ky < 0 || ky >= 7 || kx < 0 || kx >= 7 || tap >= 16) return;
   } else {
-    k = (ky * kw + kx) * cin + ci;
+    const int tap = k / cpad;
+    ci = k - tap * cpad;
+    if (tap >= kh * kw || ci >= cin) return;
+    ky = tap / kw;
+    kx = tap - ky * kw;
   }
   double s = 0.0;
   for (int sp = 0; sp < splits; ++sp) s += partial[(static_cast<size_t>(sp) * co_rows + co) * kpad + k];
-  dw[idx] = (accumulate ? dw[idx] : 0.f) + static_cast<float>(s);
+  const size_t o = ((static_cast<size_t>(co) * cin + ci) * kh + ky) * kw + kx;
+  dw[o] = (accumulate ? dw[o] : 0.f) + static_cast<float>(s);
 }
 
 struct WgradPlan { int k_chunks, chunks_per_group, k_groups, co_tiles, splits, blocks_per_split, num_pix_blocks; };
@@ -287,9 +294,10 @@ extern "C" int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* 
   FP_CHECK_LAUNCH("fp_conv_wgrad");
   const int cin = stem ? 3 : d->c0 + d->c1;
   const int kh = stem ? 7 : d->kh, kw = stem ? 7 : d->kw;
-  const long long total = static_cast<long long>(d->cout) * cin * kh * kw;
+  const long long total = static_cast<long long>(d->cout) * d->kpad;
   wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-      workspace, p.splits, p.co_tiles * 128, d->kpad, d->cout, cin, kh, kw, stem, accumulate, dw_oihw);
+      workspace, p.splits, p.co_tiles * 128, d->kpad, d->cout, cin, stem ? 16 : d->c0 + d->c1, kh, kw, stem, accumulate,
+      dw_oihw);
   FP_CHECK_LAUNCH("fp_conv_wgrad(reduce)");
   return FP_OK;
 }

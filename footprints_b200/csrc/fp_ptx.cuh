@@ -35,10 +35,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns)
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
@@ -74,11 +74,18 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // 16-byte copy, or 16 bytes of zeros when `valid` is false (the ignore-src form: no size arithmetic)
+// .ca (allocate in L1): horizontally adjacent filter taps of the im2col gather re-read the same 128-byte lines
+// shifted by one pixel, so letting them hit (or merge in) L1 cuts the L2->SM traffic of the 9x im2col re-read.
+#ifndef FP_CP_ASYNC_CG
+#define FP_CP_ASYNC_OP "cp.async.ca.shared.global"
+#else
+#define FP_CP_ASYNC_OP "cp.async.cg.shared.global"
+#endif
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t dst_smem, const void* src, bool valid) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.eq.u32 p, %2, 0;\n\t"
-      "cp.async.cg.shared.global [%0], [%1], 16, p;\n\t}"
+      FP_CP_ASYNC_OP " [%0], [%1], 16, p;\n\t}"
       ::"r"(dst_smem), "l"(src), "r"(static_cast<uint32_t>(valid))
       : "memory");
 }

@@ -1,0 +1,307 @@
+// Dedicated CUDA-core kernels for the 2-channel output heads (OutConvBlock, footprints/network.py:161-183): a
+// 3x3 reflection-padded convolution Cin -> 2.  With N = 2 the tensor-core implicit GEMM wastes >98 % of every
+// MMA (and of the 128-row weight-gradient tile), so forward, data gradient and weight gradient are plain FMA
+// kernels here: memory-bound, each input pixel is re-read from L1/L2 by its 9 neighbours.
+#include "fp_internal.h"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace fp {
+
+__device__ __forceinline__ float2 h_up2(uint32_t u, int fmt) {
+  if (fmt == FP_BF16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+__device__ __forceinline__ uint32_t h_pk2(float a, float b, int fmt) {
+  if (fmt == FP_BF16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void h_unpack8(const uint4& v, int fmt, float (&f)[8]) {
+  float2 t;
+  t = h_up2(v.x, fmt); f[0] = t.x; f[1] = t.y;
+  t = h_up2(v.y, fmt); f[2] = t.x; f[3] = t.y;
+  t = h_up2(v.z, fmt); f[4] = t.x; f[5] = t.y;
+  t = h_up2(v.w, fmt); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ int reflect1(int v, int n) { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); }
+
+constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_MAX_C = 128;
+
+// ---------------------------------------------------------------------------------------------- forward
+// One thread per (output pixel, 8-channel chunk): the c8 lanes of a pixel read 16 consecutive bytes each (coalesced),
+// accumulate their channels' share of both outputs and combine with a shuffle tree.  Weights sit in shared memory as
+// [tap][i][chunk] so that the lanes of a warp hit consecutive addresses.
+__global__ void __launch_bounds__(HEAD_THREADS)
+head_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ w /*[2][C][3][3]*/, const float* __restrict__ bias,
+                int batch, int H, int W, int C, int sigmoid, int fmt, float2* __restrict__ out) {
+  __shared__ float2 sw[9 * HEAD_MAX_C];
+  const int c8 = C >> 3;
+  for (int i = threadIdx.x; i < 9 * C; i += HEAD_THREADS) {
+    const int t = i / C, c = i - t * C;
+    sw[(t * 8 + (c & 7)) * c8 + (c >> 3)] = make_float2(w[(0 * C + c) * 9 + t], w[(1 * C + c) * 9 + t]);
+  }
+  __syncthreads();
+  const long long idx = blockIdx.x * static_cast<long long>(HEAD_THREADS) + threadIdx.x;
+  const long long P = static_cast<long long>(batch) * H * W;
+  const long long pix = idx / c8;
+  const int cc = static_cast<int>(idx - pix * c8);
+  const bool valid = pix < P;
+  float a0 = 0.f, a1 = 0.f;
+  if (valid) {
+    const int px = static_cast<int>(pix % W);
+    const int py = static_cast<int>((pix / W) % H);
+    const long long img = pix / (static_cast<long long>(W) * H) * H;
+#pragma unroll
+    for (int ty = 0; ty < 3; ++ty) {
+      const int yy = reflect1(py + ty - 1, H);
+#pragma unroll
+      for (int tx = 0; tx < 3; ++tx) {
+        const int xx = reflect1(px + tx - 1, W);
+        float f[8];
+        h_unpack8(x[((img + yy) * W + xx) * c8 + cc], fmt, f);
+        const float2* wt = sw + (ty * 3 + tx) * 8 * c8 + cc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 ww = wt[i * c8];
+          a0 = fmaf(f[i], ww.x, a0);
+          a1 = fmaf(f[i], ww.y, a1);
+        }
+      }
+    }
+  }
+  // c8 is 1, 2, 4, 8 or 16: lanes of one pixel are contiguous and aligned inside the warp
+  for (int off = c8 >> 1; off > 0; off >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+  }
+  if (valid && cc == 0) {
+    a0 += bias[0];
+    a1 += bias[1];
+    if (sigmoid) {
+      a0 = 1.f / (1.f + expf(-a0));
+      a1 = 1.f / (1.f + expf(-a1));
+    }
+    out[pix] = make_float2(a0, a1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- data gradient
+// dX[p][c] = sum over the virtual (reflection-padded) positions v that map onto p, taps t: W[co][c][t] * dZ[v - t + 1][co],
+// optionally (+ previous content of dst) and * act'(y) of the layer that produced x.  One thread per (pixel, 8 channels).
+__global__ void __launch_bounds__(HEAD_THREADS)
+head_dgrad_kernel(const uint4* __restrict__ dz8 /*[B][H][W][8] 16-bit, ch 0..1 valid*/, const float* __restrict__ w,
+                  int batch, int H, int W, int C, int accumulate, const uint4* __restrict__ yact, int act, int act_fmt,
+                  int grad_fmt, uint4* __restrict__ dst) {
+  __shared__ float2 sw[9 * HEAD_MAX_C];
+  const int c8 = C >> 3;
+  for (int i = threadIdx.x; i < 9 * C; i += HEAD_THREADS) {
+    const int t = i / C, c = i - t * C;
+    sw[(t * 8 + (c & 7)) * c8 + (c >> 3)] = make_float2(w[(0 * C + c) * 9 + t], w[(1 * C + c) * 9 + t]);
+  }
+  __syncthreads();
+  const long long idx = blockIdx.x * static_cast<long long>(HEAD_THREADS) + threadIdx.x;
+  if (idx >= static_cast<long long>(batch) * H * W * c8) return;
+  const int cc = static_cast<int>(idx % c8);
+  long long t = idx / c8;
+  const int px = static_cast<int>(t % W); t /= W;
+  const int py = static_cast<int>(t % H);
+  const long long img = t / H * H;
+  // virtual rows / columns (in [-1, H]) that reflect onto (py, px)
+  int vy[2], vx[2], ny = 1, nx = 1;
+  vy[0] = py; vx[0] = px;
+  if (py == 1) vy[ny++] = -1;
+  if (py == H - 2) vy[ny++] = H;
+  if (px == 1) vx[nx++] = -1;
+  if (px == W - 2) vx[nx++] = W;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int iy = 0; iy < ny; ++iy)
+    for (int ix = 0; ix < nx; ++ix) {
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) {
+        const int qy = vy[iy] - ty + 1;
+        if (qy < 0 || qy >= H) continue;
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx) {
+          const int qx = vx[ix] - tx + 1;
+          if (qx < 0 || qx >= W) continue;
+          const float2 g = h_up2(reinterpret_cast<const uint32_t*>(dz8 + (img + qy) * W + qx)[0], grad_fmt);
+          const float2* wt = sw + (ty * 3 + tx) * 8 * c8 + cc;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(wt[i * c8].x, g.x, fmaf(wt[i * c8].y, g.y, acc[i]));
+        }
+      }
+    }
+  if (accumulate) {
+    float f[8];
+    h_unpack8(dst[idx], grad_fmt, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += f[i];
+  }
+  if (yact != nullptr) {
+    float fy[8];
+    h_unpack8(yact[idx], act_fmt, fy);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (act == FP_ACT_ELU) acc[i] *= fy[i] > 0.f ? 1.f : fy[i] + 1.f;
+      else if (act == FP_ACT_RELU) acc[i] = fy[i] > 0.f ? acc[i] : 0.f;
+    }
+  }
+  uint4 o;
+  o.x = h_pk2(acc[0], acc[1], grad_fmt); o.y = h_pk2(acc[2], acc[3], grad_fmt);
+  o.z = h_pk2(acc[4], acc[5], grad_fmt); o.w = h_pk2(acc[6], acc[7], grad_fmt);
+  dst[idx] = o;
+}
+
+// ---------------------------------------------------------------------------------------------- weight gradient
+// Stage 1: block b reduces its pixel range; thread = (pixel sub-range g, tap t, 8-channel chunk cc) accumulates
+// 2 x 8 sums, then a fixed-order shared-memory reduction over g.  partial[b][co][c][t] (+ bias sums at the end).
+__global__ void __launch_bounds__(HEAD_THREADS)
+head_wgrad_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dz8, int batch, int H, int W, int C, int act_fmt,
+                  int grad_fmt, long long pix_per_block, float* __restrict__ partial) {
+  extern __shared__ float red[];          // [groups][lanes_per_group][16]
+  const int c8 = C >> 3;
+  const int lanes = 9 * c8;               // (tap, chunk) pairs
+  const int groups = HEAD_THREADS / lanes;
+  const int g = threadIdx.x / lanes, l = threadIdx.x - g * lanes;
+  const long long P = static_cast<long long>(batch) * H * W;
+  const long long p0 = blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  float b0 = 0.f, b1 = 0.f;
+  if (g < groups) {
+    const int t = l / c8, cc = l - t * c8;
+    const int ty = t / 3, tx = t - ty * 3;
+    constexpr int U = 4;                  // independent loads in flight per thread
+    for (long long pb = p0 + g; pb < p1; pb += static_cast<long long>(groups) * U) {
+      uint32_t dv[U];
+      uint4 xv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = pb + static_cast<long long>(u) * groups;
+        dv[u] = 0u;
+        xv[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (p < p1) {
+          const int px = static_cast<int>(p % W);
+          const int py = static_cast<int>((p / W) % H);
+          const long long img = p / (static_cast<long long>(W) * H) * H;
+          const int yy = reflect1(py + ty - 1, H), xx = reflect1(px + tx - 1, W);
+          dv[u] = reinterpret_cast<const uint32_t*>(dz8 + p)[0];
+          xv[u] = x[((img + yy) * W + xx) * c8 + cc];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float2 d = h_up2(dv[u], grad_fmt);      // zero for p >= p1
+        float f[8];
+        h_unpack8(xv[u], act_fmt, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i] = fmaf(f[i], d.x, acc[i]);
+          acc[8 + i] = fmaf(f[i], d.y, acc[8 + i]);
+        }
+        if (l == 0) { b0 += d.x; b1 += d.y; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) red[(g * lanes + l) * 16 + i] = acc[i];
+  }
+  __shared__ float redb[HEAD_THREADS / 9][2];
+  if (g < groups && l == 0) { redb[g][0] = b0; redb[g][1] = b1; }
+  __syncthreads();
+  float* out = partial + static_cast<long long>(blockIdx.x) * (2 * C * 9 + 2);
+  for (int i = threadIdx.x; i < lanes * 16; i += HEAD_THREADS) {
+    const int ll = i >> 4, j = i & 15;
+    float s = 0.f;
+    for (int gg = 0; gg < groups; ++gg) s += red[(gg * lanes + ll) * 16 + j];
+    const int t = ll / c8, cc = ll - t * c8;
+    const int co = j >> 3, c = cc * 8 + (j & 7);
+    out[(co * C + c) * 9 + t] = s;
+  }
+  if (threadIdx.x < 2) {
+    float s = 0.f;
+    for (int gg = 0; gg < groups; ++gg) s += redb[gg][threadIdx.x];
+    out[2 * C * 9 + threadIdx.x] = s;
+  }
+}
+
+// Stage 2: fixed-order sum over blocks
+__global__ void head_wgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int n, int accumulate,
+                                         float* __restrict__ dw, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n + 2) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[static_cast<long long>(b) * (n + 2) + i];
+  float* o = i < n ? dw + i : db + (i - n);
+  *o = (accumulate ? *o : 0.f) + static_cast<float>(s);
+}
+
+}  // namespace fp
+
+using namespace fp;
+
+static int head_check(const char* who, int C, int H, int W) {
+  if ((C & 7) || C > HEAD_MAX_C || C < 8) return set_error(FP_ERR_UNSUPPORTED, "%s: C=%d must be a multiple of 8 <= %d", who, C, HEAD_MAX_C);
+  if (H < 2 || W < 2) return set_error(FP_ERR_ARG, "%s: reflection padding needs H, W >= 2", who);
+  return FP_OK;
+}
+
+extern "C" int fp_head_conv_fwd(const void* x, const float* w_oihw, const float* bias, int batch, int h, int w, int c,
+                                int sigmoid, int dtype, float* out, void* stream) {
+  if (!x || !w_oihw || !bias || !out) return set_error(FP_ERR_ARG, "fp_head_conv_fwd: null argument");
+  int rc = head_check("fp_head_conv_fwd", c, h, w);
+  if (rc != FP_OK) return rc;
+  const long long n = static_cast<long long>(batch) * h * w * (c / 8);     // one thread per (pixel, 8-channel chunk)
+  head_fwd_kernel<<<static_cast<unsigned>((n + HEAD_THREADS - 1) / HEAD_THREADS), HEAD_THREADS, 0,
+                    static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), w_oihw, bias, batch, h, w, c, sigmoid,
+                                                         dtype, reinterpret_cast<float2*>(out));
+  FP_CHECK_LAUNCH("fp_head_conv_fwd");
+  return FP_OK;
+}
+
+extern "C" int fp_head_conv_dgrad(const void* dz8, const float* w_oihw, int batch, int h, int w, int c, int accumulate,
+                                  const void* y_act, int act, int act_dtype, int grad_dtype, void* dst, void* stream) {
+  if (!dz8 || !w_oihw || !dst) return set_error(FP_ERR_ARG, "fp_head_conv_dgrad: null argument");
+  int rc = head_check("fp_head_conv_dgrad", c, h, w);
+  if (rc != FP_OK) return rc;
+  const long long n = static_cast<long long>(batch) * h * w * (c / 8);
+  head_dgrad_kernel<<<static_cast<unsigned>((n + HEAD_THREADS - 1) / HEAD_THREADS), HEAD_THREADS, 0,
+                      static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(dz8), w_oihw, batch, h, w, c, accumulate,
+                                                           static_cast<const uint4*>(y_act), act, act_dtype, grad_dtype,
+                                                           static_cast<uint4*>(dst));
+  FP_CHECK_LAUNCH("fp_head_conv_dgrad");
+  return FP_OK;
+}
+
+extern "C" long long fp_head_conv_wgrad_workspace_floats(int c) { return 1184ll * (2 * c * 9 + 2); }
+
+extern "C" int fp_head_conv_wgrad(const void* x, const void* dz8, int batch, int h, int w, int c, int act_dtype,
+                                  int grad_dtype, int accumulate, float* dw_oihw, float* dbias, float* workspace,
+                                  void* stream) {
+  if (!x || !dz8 || !dw_oihw || !dbias || !workspace) return set_error(FP_ERR_ARG, "fp_head_conv_wgrad: null argument");
+  int rc = head_check("fp_head_conv_wgrad", c, h, w);
+  if (rc != FP_OK) return rc;
+  const long long P = static_cast<long long>(batch) * h * w;
+  const int lanes = 9 * (c / 8);
+  if (lanes > HEAD_THREADS) return set_error(FP_ERR_UNSUPPORTED, "fp_head_conv_wgrad: C too large");
+  const int groups = HEAD_THREADS / lanes;
+  long long want = (P + 4095) / 4096;
+  const int nblk = static_cast<int>(want < 1 ? 1 : (want > 1184 ? 1184 : want));
+  const long long ppb = (P + nblk - 1) / nblk;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  head_wgrad_kernel<<<nblk, HEAD_THREADS, groups * lanes * 16 * sizeof(float), st>>>(
+      static_cast<const uint4*>(x), static_cast<const uint4*>(dz8), batch, h, w, c, act_dtype, grad_dtype, ppb, workspace);
+  FP_CHECK_LAUNCH("fp_head_conv_wgrad");
+  const int n = 2 * c * 9;
+  head_wgrad_reduce_kernel<<<(n + 2 + 127) / 128, 128, 0, st>>>(workspace, nblk, n, accumulate, dw_oihw, dbias);
+  FP_CHECK_LAUNCH("fp_head_conv_wgrad(reduce)");
+  return FP_OK;
+}

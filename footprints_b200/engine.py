@@ -46,6 +46,7 @@ class ConvLayer:
         self.cin0, self.cin1 = cin0, cin1
         self.k, self.stride, self.pad, self.pad_mode, self.up0 = k, stride, pad, pad_mode, up0
         self.act, self.out_f32, self.stem = act, out_f32, stem
+        self.is_head = out_f32            # 2-channel output heads run on dedicated CUDA-core kernels
         self.cout = weight.shape[0]
         self.bn_tile = _bn_tile(self.cout)
         self.npad = (self.cout + self.bn_tile - 1) // self.bn_tile * self.bn_tile
@@ -159,6 +160,8 @@ class Engine:
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         dev = self.layers['stem'].weight.device
         for L in self.layers.values():
+            if L.is_head:
+                continue            # heads read the fp32 parameters directly
             w = L.weight.detach()
             if w.dtype != torch.float32 or not w.is_contiguous():
                 w = w.float().contiguous()
@@ -215,6 +218,13 @@ class Engine:
                                         _ptr(L.scale if scale is None else scale),
                                         _ptr(L.shift if shift is None else shift), _ptr(residual), _ptr(out), stream))
         self._prof_end()
+        self.launches += 1
+
+    def _head(self, L, src, out, stream):
+        """OutConvBlock conv (+ sigmoid): footprints/network.py:174-178."""
+        b, h, w, c = src.shape
+        _lib.check(self.lib.fp_head_conv_fwd(_ptr(src), _ptr(L.weight.detach()), _ptr(L.bias.detach()), b, h, w, c,
+                                             1 if L.act == FP_ACT_SIGMOID else 0, self.fmt, _ptr(out), stream))
         self.launches += 1
 
     # ------------------------------------------------------------------------------ forward (inference)
@@ -279,7 +289,7 @@ class Engine:
                 self._conv(d[f'b{bi}.post2'], t3, None, x, None, stream)
                 if bi >= 2:
                     hd = self._buf(f'{dname}.head{bi - 1}', (b, 2 * hh, 2 * ww, 2), torch.float32)
-                    self._conv(d[f'head{bi - 1}'], x, None, hd, None, stream)
+                    self._head(d[f'head{bi - 1}'], x, hd, stream)
                     heads[(dname, bi - 1)] = hd
             hh, ww = x.shape[1], x.shape[2]
             t = self._buf(f'{dname}.o4.c1', (b, 2 * hh, 2 * ww, 32))
@@ -287,7 +297,7 @@ class Engine:
             t2 = self._buf(f'{dname}.o4.c2', (b, 2 * hh, 2 * ww, 32))
             self._conv(d['o4.c2'], t, None, t2, None, stream)
             hd = self._buf(f'{dname}.head4', (b, 2 * hh, 2 * ww, 2), torch.float32)
-            self._conv(d['head4'], t2, None, hd, None, stream)
+            self._head(d['head4'], t2, hd, stream)
             heads[(dname, 4)] = hd
 
         outputs = OrderedDict()

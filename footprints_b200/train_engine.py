@@ -78,6 +78,8 @@ class TrainEngine(Engine):
         stream = self._stream()
         dev = self._dev()
         for L in self.layers.values():
+            if L.is_head:
+                continue            # heads read the fp32 parameters directly
             w = L.weight.detach()
             if L.w_packed is None:
                 L.w_packed = torch.empty((L.npad, L.kpad), dtype=self.tdtype, device=dev)
@@ -195,7 +197,7 @@ class TrainEngine(Engine):
                 sv[d[f'b{bi}.post2'].name] = (t3, None, x)
                 if bi >= 2:
                     hd = new((b, 2 * hh, 2 * ww, 2), torch.float32)
-                    self._conv(d[f'head{bi - 1}'], x, None, hd, None, stream)
+                    self._head(d[f'head{bi - 1}'], x, hd, stream)
                     sv[d[f'head{bi - 1}'].name] = (x, None, hd)
                     heads[(dname, bi - 1)] = hd
             hh, ww = x.shape[1], x.shape[2]
@@ -206,7 +208,7 @@ class TrainEngine(Engine):
             self._conv(d['o4.c2'], t, None, t2, None, stream)
             sv[d['o4.c2'].name] = (t, None, t2)
             hd = new((b, 2 * hh, 2 * ww, 2), torch.float32)
-            self._conv(d['head4'], t2, None, hd, None, stream)
+            self._head(d['head4'], t2, hd, stream)
             sv[d['head4'].name] = (t2, None, hd)
             heads[(dname, 4)] = hd
 
@@ -353,12 +355,20 @@ class TrainEngine(Engine):
                 self._wgrad(L, src0, src1, dz, grads, stream)
                 return self._dgrad_full(L, dz, stream)
 
+            def head_bwd(L, src, dzh, dst, accumulate):
+                """weight/bias gradient of a head (tensor-core wgrad: faster than the CUDA-core fp_head_conv_wgrad at
+                these sizes) and its data gradient (CUDA-core kernel: reflect adjoint + ELU' of src fused) into dst."""
+                bb, hh_, ww_, cc_ = src.shape
+                self._wgrad(L, src, None, dzh, grads, stream)
+                _lib.check(lib.fp_head_conv_dgrad(_ptr(dzh), _ptr(L.weight.detach()), bb, hh_, ww_, cc_, 1 if accumulate else 0,
+                                                  _ptr(src), FP_ACT_ELU, self.fmt, self.gfmt, _ptr(dst), stream))
+                self.launches += 1
+
             # ---- outconv4 chain at full resolution
-            L, src, dz = head_dz(4)
-            dvp = conv_bwd(L, dz)
+            L, src, dzh = head_dz(4)
             o4c2_out = src
             dz = gnew(o4c2_out.shape)
-            self._fold(dvp, h, w, 0, 32, False, dz, False, o4c2_out, FP_ACT_ELU, stream)
+            head_bwd(L, src, dzh, dz, False)
             L = d['o4.c2']
             dvp = conv_bwd(L, dz)
             o4c1_out = sv[L.name][0]
@@ -369,15 +379,14 @@ class TrainEngine(Engine):
             x = sv[L.name][0]                       # block4 output [b, h/2, w/2, 64]
             dx = gnew(x.shape)
             self._fold(dvp, h, w, 0, 64, True, dx, False, None, FP_ACT_NONE, stream)
-            del dvp, dz
+            del dvp, dz, dzh
             # ---- blocks 4..1 (each block output also feeds a head, except block1)
             for bi in range(4, 0, -1):
                 hh, ww = x.shape[1], x.shape[2]
                 co = x.shape[3]
                 if bi >= 2:
                     L, src, dzh = head_dz(bi - 1)
-                    dvp = conv_bwd(L, dzh)
-                    self._fold(dvp, hh, ww, 0, co, False, dx, True, x, FP_ACT_ELU, stream)     # + head path, then ELU'
+                    head_bwd(L, src, dzh, dx, True)                                            # + head path, then ELU'
                     dz = dx
                 else:
                     dz = gnew(x.shape)

@@ -100,6 +100,21 @@ int fp_maxpool3x3s2(const void* in, int batch, int h, int w, int c, int dtype, v
 int fp_heads_to_nchw(const float* mask_head, const float* depth_head, int batch, int h, int w, int scale,
                      float* out_nchw, void* stream);
 
+/* Heads (OutConvBlock, network.py:161-183): 3x3 reflection-padded convolution Cin -> 2 (+ Sigmoid) on CUDA cores
+ * (N = 2 wastes the tensor-core tile).  x: NHWC 16-bit [batch][h][w][c], c a multiple of 8 <= 128; w_oihw [2][c][3][3]
+ * and bias [2] are the fp32 parameters themselves; out: fp32 [batch][h][w][2] (input of fp_heads_to_nchw). */
+int fp_head_conv_fwd(const void* x, const float* w_oihw, const float* bias, int batch, int h, int w, int c, int sigmoid,
+                     int dtype, float* out, void* stream);
+/* Data gradient of that convolution including the reflection-pad adjoint: dst[p][ci] (+)= sum W[co][ci][t]*dz8[q][co]
+ * over every (q, t) whose reflected tap lands on p; then * act'(y_act) when y_act is given (ELU/ReLU derivative from
+ * the producing layer's saved output).  dz8: [batch][h][w][8] 16-bit, channels 0..1 valid (fp_heads_bwd's output). */
+int fp_head_conv_dgrad(const void* dz8, const float* w_oihw, int batch, int h, int w, int c, int accumulate,
+                       const void* y_act, int act, int act_dtype, int grad_dtype, void* dst, void* stream);
+/* Weight and bias gradient of that convolution (two-stage, deterministic). */
+long long fp_head_conv_wgrad_workspace_floats(int c);
+int fp_head_conv_wgrad(const void* x, const void* dz8, int batch, int h, int w, int c, int act_dtype, int grad_dtype,
+                       int accumulate, float* dw_oihw, float* dbias, float* workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Training step.  Replaces autograd's backward of footprints/network.py (triggered at
  * footprints/training/train.py:155), train-mode BatchNorm (torchvision resnet.py:82-104 in .train()),

@@ -267,3 +267,33 @@ def test_bias_grad_and_adam(lib):
         _lib.check(lib.fp_adam_step(P(p), P(grad), P(m), P(v), n, 1e-4, 0.9, 0.999, 1e-8, step, 1.0, None))
     torch.cuda.synchronize()
     assert (p - ref.detach()).abs().max() <= 1e-6
+
+
+@pytest.mark.parametrize('C,sigmoid', [(32, 1), (64, 0), (128, 1)])
+def test_head_kernels_match_autograd(lib, C, sigmoid):
+    """fp_head_conv_fwd / _dgrad / _wgrad (CUDA-core kernels of the 2-channel heads) against autograd."""
+    g = torch.Generator().manual_seed(8)
+    b, h, w = 2, 9, 14
+    x = rnd(b, C, h, w, g=g).requires_grad_(True)
+    wgt = rnd(2, C, 3, 3, g=g, scale=1.0 / (9 * C) ** 0.5).requires_grad_(True)
+    bias = (torch.randn(2, generator=g).cuda() * 0.1).requires_grad_(True)
+    z = F.conv2d(F.pad(x, (1, 1, 1, 1), mode='reflect'), wgt, bias)
+    y = torch.sigmoid(z) if sigmoid else z
+    dz = rnd(*z.shape, g=g)
+    z.backward(dz)
+    x16 = nhwc(x.detach())
+    out = torch.empty(b, h, w, 2, device='cuda')
+    _lib.check(lib.fp_head_conv_fwd(P(x16), P(wgt.detach()), P(bias.detach()), b, h, w, C, sigmoid, BF, P(out), None))
+    torch.cuda.synchronize()
+    assert (out.permute(0, 3, 1, 2) - y.detach()).abs().max() <= 2e-5
+    dz8 = torch.zeros(b, h, w, 8, dtype=DT, device='cuda')
+    dz8[..., :2] = nhwc(dz)
+    dw, db = torch.empty(2, C, 3, 3, device='cuda'), torch.empty(2, device='cuda')
+    wsp = torch.empty(lib.fp_head_conv_wgrad_workspace_floats(C), device='cuda')
+    _lib.check(lib.fp_head_conv_wgrad(P(x16), P(dz8), b, h, w, C, BF, BF, 0, P(dw), P(db), P(wsp), None))
+    dx = torch.empty(b, h, w, C, dtype=DT, device='cuda')
+    _lib.check(lib.fp_head_conv_dgrad(P(dz8), P(wgt.detach()), b, h, w, C, 0, None, 0, BF, BF, P(dx), None))
+    torch.cuda.synchronize()
+    assert (dw - wgt.grad).abs().max() <= 1e-4 * wgt.grad.abs().max() + 1e-5
+    assert (db - bias.grad).abs().max() <= 1e-4 * bias.grad.abs().max() + 1e-5
+    assert (nchw(dx) - x.grad).abs().max() <= 1e-2 * x.grad.abs().max()
