@@ -238,6 +238,7 @@ def main():
 
     state = {'i': 0}
     d2h = 21 * 4 if args.mode == 'train' else B * 4 * H * W * 4
+    host_out = torch.empty((B, 4, H, W), dtype=torch.float32).pin_memory() if args.mode == 'infer' else None
 
     def step_e2e():
         i = state['i']
@@ -247,7 +248,8 @@ def main():
             out = trainer.step(bufs[i]['image'], {k: bufs[i][k] for k in tkeys})
             out.cpu()                                   # D2H read of the step's losses (train.py's evaluator does this)
         else:
-            net(bufs[i]['image'])['1/1'].cpu()          # predict_simple.py:68
+            host_out.copy_(net(bufs[i]['image'])['1/1'], non_blocking=True)   # predict_simple.py:68 (pinned dst)
+            torch.cuda.current_stream().synchronize()
         copy_stream.wait_stream(torch.cuda.current_stream())
         state['i'] = 1 - i
 
@@ -299,7 +301,7 @@ def main():
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                'vs_baseline': None, 'dtype': 'bf16' if args.mode == 'train' else 'f16', 'data': 'synthetic',
                 'config': {'workload': ('training step: fwd (train-mode BN) + fused BCE/log-L1 loss + bwd + Adam' if args.mode == 'train'
                                         else 'inference forward') + f', {args.arch} encoder + 2 skip decoders, {H}x{W}, '
                                                                     f'batch {B}/GPU, random-init weights',

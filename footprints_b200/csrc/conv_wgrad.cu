@@ -228,8 +228,15 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
     ky = tap / kw;
     kx = tap - ky * kw;
   }
-  double s = 0.0;
-  for (int sp = 0; sp < splits; ++sp) s += partial[(static_cast<size_t>(sp) * co_rows + co) * kpad + k];
+  const size_t stride = static_cast<size_t>(co_rows) * kpad;
+  const float* src = partial + static_cast<size_t>(co) * kpad + k;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;        // four independent chains, fixed order
+  int sp = 0;
+  for (; sp + 4 <= splits; sp += 4) {
+    s0 += src[(sp + 0) * stride]; s1 += src[(sp + 1) * stride]; s2 += src[(sp + 2) * stride]; s3 += src[(sp + 3) * stride];
+  }
+  for (; sp < splits; ++sp) s0 += src[sp * stride];
+  const double s = (s0 + s1) + (s2 + s3);
   const size_t o = ((static_cast<size_t>(co) * cin + ci) * kh + ky) * kw + kx;
   dw[o] = (accumulate ? dw[o] : 0.f) + static_cast<float>(s);
 }

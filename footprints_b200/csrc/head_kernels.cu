@@ -91,6 +91,122 @@ head_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ w /*[2][C
   }
 }
 
+// Variant for C <= 32: one thread per output pixel (64 contiguous bytes per tap and thread, weights broadcast from
+// shared memory).  Measured 9x faster than the chunk-per-thread mapping at 192x640x32 (HBM-bound), slower for C >= 64.
+__global__ void __launch_bounds__(HEAD_THREADS)
+head_fwd_pixel_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int batch,
+                      int H, int W, int C, int sigmoid, int fmt, float2* __restrict__ out) {
+  __shared__ float2 sw[9 * 32];
+  for (int i = threadIdx.x; i < 9 * C; i += HEAD_THREADS) {
+    const int t = i / C, c = i - t * C;
+    sw[i] = make_float2(w[(0 * C + c) * 9 + t], w[(1 * C + c) * 9 + t]);
+  }
+  __syncthreads();
+  const long long idx = blockIdx.x * static_cast<long long>(HEAD_THREADS) + threadIdx.x;
+  if (idx >= static_cast<long long>(batch) * H * W) return;
+  const int px = static_cast<int>(idx % W);
+  const int py = static_cast<int>((idx / W) % H);
+  const long long img = idx / (static_cast<long long>(W) * H) * H;
+  const int c8 = C >> 3;
+  float a0 = bias[0], a1 = bias[1];
+#pragma unroll
+  for (int ty = 0; ty < 3; ++ty) {
+    const int yy = reflect1(py + ty - 1, H);
+#pragma unroll
+    for (int tx = 0; tx < 3; ++tx) {
+      const int xx = reflect1(px + tx - 1, W);
+      const uint4* src = x + ((img + yy) * W + xx) * c8;
+      const float2* wt = sw + (ty * 3 + tx) * C;
+      for (int cc = 0; cc < c8; ++cc) {
+        float f[8];
+        h_unpack8(src[cc], fmt, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 ww = wt[cc * 8 + i];
+          a0 = fmaf(f[i], ww.x, a0);
+          a1 = fmaf(f[i], ww.y, a1);
+        }
+      }
+    }
+  }
+  if (sigmoid) {
+    a0 = 1.f / (1.f + expf(-a0));
+    a1 = 1.f / (1.f + expf(-a1));
+  }
+  out[idx] = make_float2(a0, a1);
+}
+
+// Same idea for the data gradient at C == 32: one thread per pixel owns all 32 channels, so each dZ value is loaded
+// once per tap instead of once per chunk.
+__global__ void __launch_bounds__(HEAD_THREADS)
+head_dgrad_pixel32_kernel(const uint4* __restrict__ dz8, const float* __restrict__ w, int batch, int H, int W,
+                          int accumulate, const uint4* __restrict__ yact, int act, int act_fmt, int grad_fmt,
+                          uint4* __restrict__ dst) {
+  constexpr int C = 32;
+  __shared__ float2 sw[9 * C];
+  for (int i = threadIdx.x; i < 9 * C; i += HEAD_THREADS) {
+    const int t = i / C, c = i - t * C;
+    sw[i] = make_float2(w[(0 * C + c) * 9 + t], w[(1 * C + c) * 9 + t]);
+  }
+  __syncthreads();
+  const long long idx = blockIdx.x * static_cast<long long>(HEAD_THREADS) + threadIdx.x;
+  if (idx >= static_cast<long long>(batch) * H * W) return;
+  const int px = static_cast<int>(idx % W);
+  const int py = static_cast<int>((idx / W) % H);
+  const long long img = idx / (static_cast<long long>(W) * H) * H;
+  int vy[2], vx[2], ny = 1, nx = 1;
+  vy[0] = py; vx[0] = px;
+  if (py == 1) vy[ny++] = -1;
+  if (py == H - 2) vy[ny++] = H;
+  if (px == 1) vx[nx++] = -1;
+  if (px == W - 2) vx[nx++] = W;
+  float acc[C];
+#pragma unroll
+  for (int i = 0; i < C; ++i) acc[i] = 0.f;
+  for (int iy = 0; iy < ny; ++iy)
+    for (int ix = 0; ix < nx; ++ix) {
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) {
+        const int qy = vy[iy] - ty + 1;
+        if (qy < 0 || qy >= H) continue;
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx) {
+          const int qx = vx[ix] - tx + 1;
+          if (qx < 0 || qx >= W) continue;
+          const float2 g = h_up2(reinterpret_cast<const uint32_t*>(dz8 + (img + qy) * W + qx)[0], grad_fmt);
+          const float2* wt = sw + (ty * 3 + tx) * C;
+#pragma unroll
+          for (int i = 0; i < C; ++i) acc[i] = fmaf(wt[i].x, g.x, fmaf(wt[i].y, g.y, acc[i]));
+        }
+      }
+    }
+#pragma unroll
+  for (int cc = 0; cc < C / 8; ++cc) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = acc[cc * 8 + i];
+    if (accumulate) {
+      float f[8];
+      h_unpack8(dst[idx * (C / 8) + cc], grad_fmt, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += f[i];
+    }
+    if (yact != nullptr) {
+      float fy[8];
+      h_unpack8(yact[idx * (C / 8) + cc], act_fmt, fy);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (act == FP_ACT_ELU) a[i] *= fy[i] > 0.f ? 1.f : fy[i] + 1.f;
+        else if (act == FP_ACT_RELU) a[i] = fy[i] > 0.f ? a[i] : 0.f;
+      }
+    }
+    uint4 o;
+    o.x = h_pk2(a[0], a[1], grad_fmt); o.y = h_pk2(a[2], a[3], grad_fmt);
+    o.z = h_pk2(a[4], a[5], grad_fmt); o.w = h_pk2(a[6], a[7], grad_fmt);
+    dst[idx * (C / 8) + cc] = o;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- data gradient
 // dX[p][c] = sum over the virtual (reflection-padded) positions v that map onto p, taps t: W[co][c][t] * dZ[v - t + 1][co],
 // optionally (+ previous content of dst) and * act'(y) of the layer that produced x.  One thread per (pixel, 8 channels).
@@ -259,10 +375,16 @@ extern "C" int fp_head_conv_fwd(const void* x, const float* w_oihw, const float*
   if (!x || !w_oihw || !bias || !out) return set_error(FP_ERR_ARG, "fp_head_conv_fwd: null argument");
   int rc = head_check("fp_head_conv_fwd", c, h, w);
   if (rc != FP_OK) return rc;
-  const long long n = static_cast<long long>(batch) * h * w * (c / 8);     // one thread per (pixel, 8-channel chunk)
-  head_fwd_kernel<<<static_cast<unsigned>((n + HEAD_THREADS - 1) / HEAD_THREADS), HEAD_THREADS, 0,
-                    static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), w_oihw, bias, batch, h, w, c, sigmoid,
-                                                         dtype, reinterpret_cast<float2*>(out));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c <= 32) {
+    const long long n = static_cast<long long>(batch) * h * w;             // one thread per pixel
+    head_fwd_pixel_kernel<<<static_cast<unsigned>((n + HEAD_THREADS - 1) / HEAD_THREADS), HEAD_THREADS, 0, st>>>(
+        static_cast<const uint4*>(x), w_oihw, bias, batch, h, w, c, sigmoid, dtype, reinterpret_cast<float2*>(out));
+  } else {
+    const long long n = static_cast<long long>(batch) * h * w * (c / 8);   // one thread per (pixel, 8-channel chunk)
+    head_fwd_kernel<<<static_cast<unsigned>((n + HEAD_THREADS - 1) / HEAD_THREADS), HEAD_THREADS, 0, st>>>(
+        static_cast<const uint4*>(x), w_oihw, bias, batch, h, w, c, sigmoid, dtype, reinterpret_cast<float2*>(out));
+  }
   FP_CHECK_LAUNCH("fp_head_conv_fwd");
   return FP_OK;
 }
@@ -272,11 +394,18 @@ extern "C" int fp_head_conv_dgrad(const void* dz8, const float* w_oihw, int batc
   if (!dz8 || !w_oihw || !dst) return set_error(FP_ERR_ARG, "fp_head_conv_dgrad: null argument");
   int rc = head_check("fp_head_conv_dgrad", c, h, w);
   if (rc != FP_OK) return rc;
-  const long long n = static_cast<long long>(batch) * h * w * (c / 8);
-  head_dgrad_kernel<<<static_cast<unsigned>((n + HEAD_THREADS - 1) / HEAD_THREADS), HEAD_THREADS, 0,
-                      static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(dz8), w_oihw, batch, h, w, c, accumulate,
-                                                           static_cast<const uint4*>(y_act), act, act_dtype, grad_dtype,
-                                                           static_cast<uint4*>(dst));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c == 32) {
+    const long long n = static_cast<long long>(batch) * h * w;
+    head_dgrad_pixel32_kernel<<<static_cast<unsigned>((n + HEAD_THREADS - 1) / HEAD_THREADS), HEAD_THREADS, 0, st>>>(
+        static_cast<const uint4*>(dz8), w_oihw, batch, h, w, accumulate, static_cast<const uint4*>(y_act), act, act_dtype,
+        grad_dtype, static_cast<uint4*>(dst));
+  } else {
+    const long long n = static_cast<long long>(batch) * h * w * (c / 8);
+    head_dgrad_kernel<<<static_cast<unsigned>((n + HEAD_THREADS - 1) / HEAD_THREADS), HEAD_THREADS, 0, st>>>(
+        static_cast<const uint4*>(dz8), w_oihw, batch, h, w, c, accumulate, static_cast<const uint4*>(y_act), act, act_dtype,
+        grad_dtype, static_cast<uint4*>(dst));
+  }
   FP_CHECK_LAUNCH("fp_head_conv_dgrad");
   return FP_OK;
 }
