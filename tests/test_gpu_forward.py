@@ -157,3 +157,17 @@ def test_rejects_bad_shapes():
     net = _net('resnet34', 'fp16')
     with pytest.raises(RuntimeError, match='multiples of 32'):
         net(torch.rand(1, 3, 190, 638, device='cuda'))
+
+
+def test_matterport_shape_512x640_resnet18():
+    """BASELINE.json configs[4] geometry (512x640) with the ResNet-18 encoder variant: eval forward against the oracle
+    (ragged M tiles at every stage: 512x640 is not the KITTI aspect)."""
+    net = _net('resnet18', 'fp16')
+    data = synthetic_batch(2, 512, 640, 7)
+    out = net(data['image'].cuda())
+    with torch.no_grad():
+        ref = O.network_forward(synthetic_state_dict('resnet18', 0), data['image'], 'resnet18', training=False)
+    for k in out:
+        assert out[k].shape == (2, 4, 512, 640)
+        err = (out[k].cpu() - ref[k]).abs().max().item()
+        assert err <= TOL['fp16'][k], (k, err)
