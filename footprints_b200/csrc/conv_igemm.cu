@@ -36,7 +36,14 @@ constexpr int NUM_THREADS = (EPI_FIRST_WARP + NUM_EPI_WARPS) * 32;   // 544
 constexpr int ROWS_PER_THREAD = BM / (NUM_PRODUCER_THREADS / 8);     // 4
 constexpr int KTAB_ENTRIES = 1024;   // one entry per 16-byte K chunk: kpad <= 8192
 
-// perf triage (FP_DEBUG_FLAGS & 16): CTA 0 records clock64() stamps: [role][event idx]
+// perf triage hooks (FP_DEBUG_FLAGS: 1 skip A gather, 2 skip MMA, 4 skip epilogue math, 8 skip B load, 16 record
+// clock64() stamps of CTA 0 into g_trace[role][event]) are compiled in only with -DFP_TRIAGE (make TRIAGE=1):
+// even as dead branches they cost instructions in the producers' latency-bound K loop.
+#ifdef FP_TRIAGE
+constexpr bool kTriage = true;
+#else
+constexpr bool kTriage = false;
+#endif
 __device__ long long g_trace[3][2048];
 
 template <int BN>
@@ -253,7 +260,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
           const int s = it % STAGES;
           if (lane == 0) {
             mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1, 1);
-            if ((p.debug & 16) && blockIdx.x == 0 && it < 2048) g_trace[0][it] = clock64();
+            if ((kTriage && p.debug & 16) && blockIdx.x == 0 && it < 2048) g_trace[0][it] = clock64();
             mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + (p.b_via_tma ? B_STAGE_BYTES : 0));
             if (p.b_via_tma)
               tma_load_2d(smem_u32(b_smem) + s * B_STAGE_BYTES, &tmap_w, &full_bar[s], kb * BK, n_tile * BN);
@@ -277,6 +284,13 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
     const uint32_t a_dst0 = smem_u32(a_smem) + swz;
     const uint32_t b_dst0 = smem_u32(b_smem) + swz;
     uint32_t it = 0, ti = 0;
+    int s = 0;                 // running stage index and phase (no div/mod in the K loop)
+    uint32_t ph = 0;
+    // per-source constants of the gather (selected per K chunk by the table's source bit)
+    const uint8_t* const sbase0 = p.g.src0;
+    const uint8_t* const sbase1 = p.g.src1;
+    const uint32_t pstride0 = p.g.C0, pstride1 = p.g.C1;
+    const uint32_t rstride0 = p.g.W0 * p.g.C0, rstride1 = p.g.Win * p.g.C1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
@@ -293,14 +307,12 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
       for (int i = 0; i < ROWS_PER_THREAD; ++i) info[i] = info_buf[r0 + 32 * i];
 
       for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1, 1);
-        __syncwarp();
-        if ((p.debug & 16) && blockIdx.x == 0 && tid == 0 && it < 2048) g_trace[0][it] = clock64();
+        // every lane polls (uniform, no divergence); the slot is almost always free already
+        mbar_wait(&empty_bar[s], ph ^ 1, 1);
+        if ((kTriage && p.debug & 16) && blockIdx.x == 0 && tid == 0 && it < 2048) g_trace[0][it] = clock64();
         if (p.b_via_tma) {
           if (tid == 0) {
-            if (p.debug & 8) mbar_arrive(&full_bar[s]);
+            if (kTriage && p.debug & 8) mbar_arrive(&full_bar[s]);
             else {
               mbar_arrive_expect_tx(&full_bar[s], B_STAGE_BYTES);
               tma_load_2d(smem_u32(b_smem) + s * B_STAGE_BYTES, &tmap_w, &full_bar[s], kb * BK, n_tile * BN);
@@ -315,9 +327,16 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
           }
         }
         // decode this thread's K chunk (tap, channel slice, source) from the table built at kernel start
-        const KDecode kd = decode_ktab(p.g, s_ktab[kb * 8 + c]);
+        const uint32_t ke = s_ktab[kb * 8 + c];
+        KDecode kd;
+        kd.second = (ke & (1u << 10)) != 0u;
+        kd.padmask = (ke >> 8) & 8u;
+        kd.shy = ke & 31u; kd.shx = (ke >> 5) & 31u; kd.cc = ke >> 12;
+        kd.sbase = kd.second ? sbase1 : sbase0;
+        kd.pstride = kd.second ? pstride1 : pstride0;
+        kd.rstride = kd.second ? rstride1 : rstride0;
         const uint32_t dst = a_dst0 + s * A_STAGE_BYTES;
-        if (!(p.debug & 1)) {
+        if (!(kTriage && p.debug & 1)) {
 #pragma unroll
           for (int i = 0; i < ROWS_PER_THREAD; ++i) {
             bool ok;
@@ -327,6 +346,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
         }
         // the stage is published to the MMA warp when every producer thread's copies have landed
         cp_async_mbar_arrive_noinc(&full_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == MMA_WARP) {
@@ -342,13 +362,13 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&full_bar[s], (it / STAGES) & 1, 3);
-          if ((p.debug & 16) && blockIdx.x == 0 && it < 2048) g_trace[1][it] = clock64();
+          if ((kTriage && p.debug & 16) && blockIdx.x == 0 && it < 2048) g_trace[1][it] = clock64();
           tcgen05_fence_after();
           const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(a_smem) + s * A_STAGE_BYTES, 16, 1024);
           const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(b_smem) + s * B_STAGE_BYTES, 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            if (p.debug & 2) break;
+            if (kTriage && p.debug & 2) break;
             // advancing 16 K-elements = 32 bytes inside the swizzle row = +2 in the (addr >> 4) field
             umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
@@ -381,13 +401,13 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
       }
       named_bar_sync(1, NUM_EPI_THREADS);
       mbar_wait<128>(&tmem_full_bar[acc], (ti >> 1) & 1, 4);
-      if ((p.debug & 16) && blockIdx.x == 0 && e == 0 && ti < 1024) g_trace[2][2 * ti] = clock64();
+      if ((kTriage && p.debug & 16) && blockIdx.x == 0 && e == 0 && ti < 1024) g_trace[2][2 * ti] = clock64();
       tcgen05_fence_after();
       const int m = m_tile * BM + row;
       const bool m_ok = m < p.g.M;
       if (active) {
         const uint32_t tbase = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-        const bool skip = (p.debug & 4) != 0;
+        const bool skip = (kTriage && p.debug & 4) != 0;
 #define FP_EPI(A, F) epilogue_cols<A, F>(p, tbase, col_begin, COLS_PER_HALF, n_tile * BN, m, m_ok && !skip, s_scale, s_shift)
         if (p.fmt == FP_BF16) {
           switch (p.act) {
@@ -408,7 +428,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
       }
       tcgen05_fence_before();
       __syncwarp();
-      if ((p.debug & 16) && blockIdx.x == 0 && e == 0 && ti < 1024) g_trace[2][2 * ti + 1] = clock64();
+      if ((kTriage && p.debug & 16) && blockIdx.x == 0 && e == 0 && ti < 1024) g_trace[2][2 * ti + 1] = clock64();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
