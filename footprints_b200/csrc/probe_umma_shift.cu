@@ -1,0 +1,96 @@
+// Hardware probe (not part of the library): can a K-major SWIZZLE_128B UMMA operand start at a 128-byte row that is
+// not a multiple of 8 rows from the 1024-byte-aligned swizzle pattern?  If so, the three horizontal taps of a 3x3
+// convolution can share one staged row strip (descriptor start advanced by one row per tap) instead of three fills.
+//   usage: probe_umma_shift        prints, per (shift, base_offset mode), whether D[m][n] == A[m + shift][n]
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "fp_ptx.cuh"
+
+using namespace fp;
+
+constexpr int STRIP_ROWS = 144;   // 128 + 16 spare rows
+
+__global__ void __launch_bounds__(128) probe_kernel(const __half* a_gl /*[144][64]*/, const __half* b_gl /*[16][64]*/,
+                                                    int shift, int base_offset_mode, float* d_out /*[128][16]*/) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* a_s = smem;                       // 144 rows x 128 B
+  uint8_t* b_s = smem + 18432 + 1024 - (18432 % 1024);   // next 1024-aligned
+  uint64_t* bar = reinterpret_cast<uint64_t*>(b_s + 2048);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // fill A and B with the canonical SW128 pattern by ABSOLUTE position: 16-byte chunk c of row r -> c ^ (r & 7)
+  for (int i = tid; i < STRIP_ROWS * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(a_s + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(a_gl + r * 64 + c * 8);
+  }
+  for (int i = tid; i < 16 * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(b_s + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(b_gl + r * 64 + c * 8);
+  }
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tptr, 32);
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tptr;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, 16, 0, 0, 0, 0);
+    const uint32_t a_addr = smem_u32(a_s) + shift * 128;
+    uint64_t a_desc = umma_smem_desc_sw128(a_addr, 16, 1024);
+    if (base_offset_mode == 1) a_desc |= static_cast<uint64_t>((a_addr >> 7) & 7) << 49;
+    const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(b_s), 16, 1024);
+    for (int k = 0; k < 4; ++k) umma_f16(tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, k != 0);
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0, 99);
+  tcgen05_fence_after();
+  uint32_t v[16];
+  tmem_ld_32x32b_x16(tmem + (static_cast<uint32_t>(warp * 32) << 16), v);
+  tmem_ld_wait();
+  for (int x = 0; x < 16; ++x) d_out[(warp * 32 + (tid & 31)) * 16 + x] = __uint_as_float(v[x]);
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
+int main() {
+  std::vector<__half> a(STRIP_ROWS * 64), b(16 * 64);
+  // A[r][k] = 4*r + (k / 16) for k < 64 restricted to the probed columns; B = 16 selected columns: n -> k = 4*n + 1
+  for (int r = 0; r < STRIP_ROWS; ++r)
+    for (int k = 0; k < 64; ++k) a[r * 64 + k] = __float2half(static_cast<float>((r * 64 + k) % 2048));
+  for (int n = 0; n < 16; ++n)
+    for (int k = 0; k < 64; ++k) b[n * 64 + k] = __float2half(k == 4 * n + 1 ? 1.f : 0.f);
+  __half *da, *db; float* dd;
+  cudaMalloc(&da, a.size() * 2); cudaMalloc(&db, b.size() * 2); cudaMalloc(&dd, 128 * 16 * 4);
+  cudaMemcpy(da, a.data(), a.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, b.data(), b.size() * 2, cudaMemcpyHostToDevice);
+  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+  std::vector<float> d(128 * 16);
+  for (int mode = 0; mode < 2; ++mode)
+    for (int shift = 0; shift <= 9; ++shift) {
+      cudaMemset(dd, 0, 128 * 16 * 4);
+      probe_kernel<<<1, 128, 32768>>>(da, db, shift, mode, dd);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("mode %d shift %d: CUDA error %s\n", mode, shift, cudaGetErrorString(e)); return 1; }
+      cudaMemcpy(d.data(), dd, d.size() * 4, cudaMemcpyDeviceToHost);
+      int bad = 0, first = -1;
+      for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < 16; ++n) {
+          const float expect = static_cast<float>(((m + shift) * 64 + 4 * n + 1) % 2048);
+          if (d[m * 16 + n] != expect) { if (first < 0) first = m * 16 + n; ++bad; }
+        }
+      printf("base_offset_mode %d shift %d: %s (%d/2048 wrong", mode, shift, bad ? "MISMATCH" : "OK", bad);
+      if (bad) printf("; first at m=%d n=%d got %.0f want %.0f; row0: %.0f %.0f row1: %.0f row7: %.0f row8: %.0f", first / 16, first % 16,
+                      d[first], static_cast<float>(((first / 16 + shift) * 64 + 4 * (first % 16) + 1) % 2048), d[0], d[1], d[16], d[7 * 16], d[8 * 16]);
+      printf(")\n");
+    }
+  return 0;
+}
