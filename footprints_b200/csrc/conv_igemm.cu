@@ -462,6 +462,259 @@ static int launch_igemm(const IgemmParams& p, const CUtensorMap& tmap, const CUt
   return FP_OK;
 }
 
+// ==================================================================================================
+// Row-strip variant for 3x3 stride-1 convolutions on wide images (the 96x320 / 192x640 layers that carry most of
+// the network's FLOPs).  A tile is 128 consecutive output pixels of ONE image row.  For each filter row dy and each
+// 64-channel block the producers stage the input row segment once — 130 pixels x 64 channels, 128-byte rows, 128B
+// swizzle — and the three horizontal taps dx = 0,1,2 are three UMMA operands that start 0, 1 and 2 rows (128 bytes)
+// into that strip: the tensor core applies the swizzle to absolute shared-memory addresses (probe_umma_shift.cu),
+// so a K-major SW128 descriptor may begin at any 128-byte row.  Shared-memory fills and L2->SM traffic drop from 9 to
+// 3 (+1.6 %) per tile, which is what bounds these layers.  Padding (zero / reflection), the nearest x2 upsample of
+// source 0 and the channel concat are resolved per strip pixel exactly as in the general kernel.
+// ==================================================================================================
+constexpr int STRIP_PIX = BM + 2;            // 130 input pixels feed 128 outputs of a 3-tap row
+constexpr int STRIP_ROWS = 136;              // rounded up to whole 8-row swizzle groups
+constexpr int STRIP_A_BYTES = STRIP_ROWS * 128;
+
+template <int BN>
+struct StripCfg {
+  static constexpr int B_BYTES = 3 * BN * BK * 2;                      // weights of the three dx taps
+  static constexpr int STAGE_BYTES = STRIP_A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 32) ? 6 : (BN <= 64 ? 5 : 3);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 2 * BN * 4 +
+                                    2 * (2 * STRIP_ROWS + 8) * 4;
+};
+
+struct StripParams {
+  IgemmParams b;             // geometry, epilogue, tile counts (m_tiles = batch*Ho*tiles_per_row)
+  int tiles_per_row;         // ceil(Wo / 128)
+  int cblocks;               // (C0 + C1) / 64
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_constant__ CUtensorMap tmap_w) {
+  using Cfg = StripCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  const IgemmParams& p = sp.b;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* stage0 = smem;                                               // [STAGES][strip | B0 | B1 | B2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_scale = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* s_shift = s_scale + BN;
+  // per tile: element offset of every strip pixel inside its source row (0xFFFFFFFF = padding zero), for both
+  // sources, and the element offset of the three source rows (double-buffered)
+  uint32_t* s_xoff = reinterpret_cast<uint32_t*>(s_shift + BN);        // [2][2*STRIP_ROWS + 8]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], NUM_PRODUCER_THREADS + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int stages_per_tile = 3 * sp.cblocks;
+
+  if (warp < NUM_PRODUCER_WARPS) {
+    // =============================== PRODUCERS ===============================
+    const int c = tid & 7;     // 16-byte chunk of the 128-byte strip row
+    const int r0 = tid >> 3;   // strip rows r0 + 32*i
+    uint32_t ti = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    const GatherGeom& g = p.g;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const int xseg = m_tile % sp.tiles_per_row;
+      const int yrow = m_tile / sp.tiles_per_row;          // b * Ho + y
+      const int img = yrow / g.Ho;
+      const int y = yrow - img * g.Ho;
+      const int x0 = xseg * BM;
+      uint32_t* xo = s_xoff + (ti & 1) * (2 * STRIP_ROWS + 8);
+      if (tid < STRIP_ROWS) {
+        // column map of strip pixel j: virtual x = x0 - pad_l + j
+        int vx = x0 - g.pad_l + tid;
+        bool ok = tid < STRIP_PIX;
+        if (g.pad_mode == FP_PAD_REFLECT) vx = vx < 0 ? -vx : (vx >= g.Win ? 2 * g.Win - 2 - vx : vx);
+        ok = ok && static_cast<unsigned>(vx) < static_cast<unsigned>(g.Win);
+        xo[tid] = ok ? static_cast<uint32_t>((g.up0 ? vx >> 1 : vx) * g.C0) : 0xFFFFFFFFu;
+        xo[STRIP_ROWS + tid] = ok ? static_cast<uint32_t>(vx * g.C1) : 0xFFFFFFFFu;
+      } else if (tid < STRIP_ROWS + 3) {
+        // row map of filter row dy: virtual y = y - pad_t + dy -> element offset of that source row
+        const int dy = tid - STRIP_ROWS;
+        int vy = y - g.pad_t + dy;
+        if (g.pad_mode == FP_PAD_REFLECT) vy = vy < 0 ? -vy : (vy >= g.Hin ? 2 * g.Hin - 2 - vy : vy);
+        const bool ok = static_cast<unsigned>(vy) < static_cast<unsigned>(g.Hin);
+        xo[2 * STRIP_ROWS + dy] = ok ? static_cast<uint32_t>(((img * g.H0 + (g.up0 ? vy >> 1 : vy)) * g.W0) * g.C0) : 0xFFFFFFFFu;
+        xo[2 * STRIP_ROWS + 4 + dy] = ok ? static_cast<uint32_t>(((img * g.Hin + vy) * g.Win) * g.C1) : 0xFFFFFFFFu;
+      }
+      named_bar_sync(2, NUM_PRODUCER_THREADS);
+      for (int dy = 0; dy < 3; ++dy) {
+        for (int cb = 0; cb < sp.cblocks; ++cb) {
+          mbar_wait(&empty_bar[s], ph ^ 1, 21);
+          const uint32_t stage = smem_u32(stage0) + s * Cfg::STAGE_BYTES;
+          if (tid == 0) {
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              tma_load_2d(stage + STRIP_A_BYTES + dx * BN * 128, &tmap_w, &full_bar[s],
+                          ((dy * 3 + dx) * sp.cblocks + cb) * BK, n_tile * BN);
+          }
+          const int ch = cb * 64;
+          const bool second = ch >= g.C0;
+          const uint8_t* sbase = second ? g.src1 : g.src0;
+          const uint32_t rowoff = xo[2 * STRIP_ROWS + (second ? 4 : 0) + dy];
+          const uint32_t* xcol = xo + (second ? STRIP_ROWS : 0);
+          const uint32_t cc = static_cast<uint32_t>(second ? ch - g.C0 : ch) + c * 8;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const int r = r0 + 32 * i;
+            if (r < STRIP_PIX) {
+              const uint32_t xoff = xcol[r];
+              const bool ok = (rowoff != 0xFFFFFFFFu) && (xoff != 0xFFFFFFFFu);
+              const uint32_t off = ok ? rowoff + xoff + cc : 0u;
+              cp_async_16_zfill(stage + r * 128 + ((c ^ (r & 7)) << 4), sbase + static_cast<size_t>(off) * 2, ok);
+            }
+          }
+          cp_async_mbar_arrive_noinc(&full_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // =============================== MMA ISSUER ===============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(BM, BN, p.fmt, p.w_fmt, 0, 0);
+      uint32_t ti = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+        const uint32_t acc = ti & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1, 22);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int st = 0; st < stages_per_tile; ++st) {
+          mbar_wait(&full_bar[s], ph, 23);
+          tcgen05_fence_after();
+          const uint32_t stage = smem_u32(stage0) + s * Cfg::STAGE_BYTES;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            // the tap's A operand = the strip advanced by dx pixels (rows of 128 bytes)
+            const uint64_t a_desc = umma_smem_desc_sw128(stage + dx * 128, 16, 1024);
+            const uint64_t b_desc = umma_smem_desc_sw128(stage + STRIP_A_BYTES + dx * BN * 128, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (st | dx | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== EPILOGUE ===============================
+    const int q = warp & 3;
+    const int half = (warp - EPI_FIRST_WARP) >> 2;
+    const int row = q * 32 + lane;
+    const int e = tid - EPI_FIRST_WARP * 32;
+    constexpr int COLS_PER_HALF = (BN >= 32) ? BN / 2 : BN;
+    const int col_begin = (BN >= 32) ? half * COLS_PER_HALF : 0;
+    const bool active = (BN >= 32) || (half == 0);
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const int xseg = m_tile % sp.tiles_per_row;
+      const int yrow = m_tile / sp.tiles_per_row;
+      const int x0 = xseg * BM;
+      const uint32_t acc = ti & 1;
+      named_bar_sync(1, NUM_EPI_THREADS);
+      for (int j = e; j < BN; j += NUM_EPI_THREADS) {
+        const int n = n_tile * BN + j;
+        s_scale[j] = (p.scale != nullptr && n < p.N) ? p.scale[n] : 1.f;
+        s_shift[j] = (p.shift != nullptr && n < p.N) ? p.shift[n] : 0.f;
+      }
+      named_bar_sync(1, NUM_EPI_THREADS);
+      mbar_wait<128>(&tmem_full_bar[acc], (ti >> 1) & 1, 24);
+      tcgen05_fence_after();
+      const int m = yrow * p.g.Wo + x0 + row;
+      const bool m_ok = (x0 + row) < p.g.Wo;
+      if (active) {
+        const uint32_t tbase = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#define FP_EPI(A, F) epilogue_cols<A, F>(p, tbase, col_begin, COLS_PER_HALF, n_tile * BN, m, m_ok, s_scale, s_shift)
+        if (p.fmt == FP_BF16) {
+          switch (p.act) {
+            case FP_ACT_RELU: FP_EPI(FP_ACT_RELU, FP_BF16); break;
+            case FP_ACT_ELU: FP_EPI(FP_ACT_ELU, FP_BF16); break;
+            case FP_ACT_SIGMOID: FP_EPI(FP_ACT_SIGMOID, FP_BF16); break;
+            default: FP_EPI(FP_ACT_NONE, FP_BF16); break;
+          }
+        } else {
+          switch (p.act) {
+            case FP_ACT_RELU: FP_EPI(FP_ACT_RELU, FP_F16); break;
+            case FP_ACT_ELU: FP_EPI(FP_ACT_ELU, FP_F16); break;
+            case FP_ACT_SIGMOID: FP_EPI(FP_ACT_SIGMOID, FP_F16); break;
+            default: FP_EPI(FP_ACT_NONE, FP_F16); break;
+          }
+        }
+#undef FP_EPI
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_strip(const StripParams& sp, const CUtensorMap& tmap, cudaStream_t stream) {
+  using Cfg = StripCfg<BN>;
+  static bool attr_set = false;
+  auto kern = conv_igemm_strip_kernel<BN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(strip smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = sp.b.total_tiles < num_sms() ? sp.b.total_tiles : num_sms();
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(sp, tmap);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "conv_igemm_strip launch (BN=%d): %s", BN, cudaGetErrorString(e));
+  return FP_OK;
+}
+
 static int ilog2_exact(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -549,6 +802,28 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
     }
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // row-strip kernel: 3x3 stride-1, 64-channel blocks, wide rows (>= 80 % of the 128-pixel row segments are used)
+  {
+    const char* senv = getenv("FP_STRIP");
+    const int segs = (d->wo + BM - 1) / BM;
+    const bool strip_ok = d->kh == 3 && d->kw == 3 && d->stride == 1 && d->up0 != 2 && (d->c0 % 64 == 0) && (d->c1 % 64 == 0) &&
+                          d->b_via_tma && d->bn <= 128 && d->bn >= 32 && d->kpad == 9 * (d->c0 + d->c1) &&
+                          d->wo * 5 >= segs * BM * 4 && !(senv && atoi(senv) == 0);
+    if (strip_ok) {
+      StripParams sp{};
+      sp.b = p;
+      sp.tiles_per_row = segs;
+      sp.cblocks = (d->c0 + d->c1) / 64;
+      sp.b.m_tiles = d->batch * d->ho * segs;
+      sp.b.total_tiles = sp.b.m_tiles * sp.b.n_tiles;
+      switch (d->bn) {
+        case 32: return launch_strip<32>(sp, tmap, st);
+        case 64: return launch_strip<64>(sp, tmap, st);
+        case 128: return launch_strip<128>(sp, tmap, st);
+        default: break;
+      }
+    }
+  }
   switch (d->bn) {
     case 16: return launch_igemm<16>(p, tmap, tmap_a0, tmap_a1, st);
     case 32: return launch_igemm<32>(p, tmap, tmap_a0, tmap_a1, st);

@@ -211,6 +211,12 @@ static const Case kCases[] = {
     {"c512_bn256_two_ntiles",        2, 512, 6, 20, 0, 0, 3, 1, 1, 0, 512, 256, 1, 0, 0, 1, 1, 1},
     {"s2d_like_c16_4x4",             2, 16, 24, 40, 0, 0, 4, 1, 2, 0, 64, 64, 1, 0, 0, 0, 1, 1},
     {"multi_tile_persistent",        8, 64, 48, 160, 0, 0, 3, 1, 1, 0, 64, 64, 1, 0, 0, 1, 1, 1},
+    // wide rows -> row-strip kernel (shifted UMMA descriptors)
+    {"strip_reflect_c64_w320",       1, 64, 6, 320, 0, 0, 3, 1, 1, 1, 64, 64, 2, 0, 0, 0, 0, 1},
+    {"strip_upcat_reflect_w320",     1, 64, 3, 160, 1, 64, 3, 1, 1, 1, 64, 64, 2, 0, 0, 0, 0, 1},
+    {"strip_fullcorr_pad2_w322",     2, 64, 5, 320, 0, 0, 3, 1, 2, 0, 128, 128, 0, 1, 0, 1, 1, 1},
+    {"strip_c128_bn32_zero_w640",    1, 128, 4, 640, 0, 0, 3, 1, 1, 0, 32, 32, 1, 0, 0, 0, 1, 1},
+    {"strip_up_c64_bn32_w640",       2, 64, 3, 320, 1, 0, 3, 1, 1, 1, 32, 32, 2, 0, 0, 0, 0, 1},
 };
 static const Case kPerf[] = {
     {"perf_layer1_64x48x160_c64",    64, 64, 48, 160, 0, 0, 3, 1, 1, 0, 64, 64, 1, 0, 0, 1, 1, 1},
