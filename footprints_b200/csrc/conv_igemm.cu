@@ -474,13 +474,17 @@ static int launch_igemm(const IgemmParams& p, const CUtensorMap& tmap, const CUt
 // ==================================================================================================
 constexpr int STRIP_PIX = BM + 2;            // 130 input pixels feed 128 outputs of a 3-tap row
 constexpr int STRIP_ROWS = 136;              // rounded up to whole 8-row swizzle groups
-constexpr int STRIP_A_BYTES = STRIP_ROWS * 128;
 
-template <int BN>
+// CB = channels per strip row: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B — the 32-channel
+// layers of the 192x640 tail; both layouts verified by probe_umma_shift.cu)
+template <int BN, int CB>
 struct StripCfg {
-  static constexpr int B_BYTES = 3 * BN * BK * 2;                      // weights of the three dx taps
-  static constexpr int STAGE_BYTES = STRIP_A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 32) ? 6 : (BN <= 64 ? 5 : 3);
+  static constexpr int ROW_BYTES = CB * 2;
+  static constexpr int A_BYTES = (STRIP_ROWS * ROW_BYTES + 1023) / 1024 * 1024;
+  static constexpr int B_TILE = BN * ROW_BYTES;                        // one dx tap's weights [BN][CB]
+  static constexpr int B_BYTES = 3 * B_TILE;
+  static constexpr int STAGE_BYTES = A_BYTES + (B_BYTES + 1023) / 1024 * 1024;
+  static constexpr int STAGES = (CB == 32) ? 8 : ((BN <= 32) ? 6 : (BN <= 64 ? 5 : 3));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 2 * BN * 4 +
                                     2 * (2 * STRIP_ROWS + 8) * 4;
@@ -489,13 +493,18 @@ struct StripCfg {
 struct StripParams {
   IgemmParams b;             // geometry, epilogue, tile counts (m_tiles = batch*Ho*tiles_per_row)
   int tiles_per_row;         // ceil(Wo / 128)
-  int cblocks;               // (C0 + C1) / 64
+  int cblocks;               // (C0 + C1) / CB
 };
 
-template <int BN>
+template <int BN, int CB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_constant__ CUtensorMap tmap_w) {
-  using Cfg = StripCfg<BN>;
+  using Cfg = StripCfg<BN, CB>;
+  constexpr int ROW_BYTES = Cfg::ROW_BYTES;
+  constexpr int CPR = ROW_BYTES / 16;                    // 16-byte chunks per strip row
+  constexpr int ROWS_PER_PASS = NUM_PRODUCER_THREADS / CPR;
+  constexpr uint64_t LAYOUT = (CB == 64) ? 2ull : 4ull;  // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
+  constexpr uint32_t SBO = 8 * ROW_BYTES;                // 8-row swizzle group
   constexpr int STAGES = Cfg::STAGES;
   const IgemmParams& p = sp.b;
 
@@ -539,8 +548,8 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
 
   if (warp < NUM_PRODUCER_WARPS) {
     // =============================== PRODUCERS ===============================
-    const int c = tid & 7;     // 16-byte chunk of the 128-byte strip row
-    const int r0 = tid >> 3;   // strip rows r0 + 32*i
+    const int c = tid % CPR;   // 16-byte chunk of the strip row
+    const int r0 = tid / CPR;  // strip rows r0 + ROWS_PER_PASS*i
     uint32_t ti = 0;
     int s = 0;
     uint32_t ph = 0;
@@ -580,23 +589,25 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
             mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES);
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx)
-              tma_load_2d(stage + STRIP_A_BYTES + dx * BN * 128, &tmap_w, &full_bar[s],
-                          ((dy * 3 + dx) * sp.cblocks + cb) * BK, n_tile * BN);
+              tma_load_2d(stage + Cfg::A_BYTES + dx * Cfg::B_TILE, &tmap_w, &full_bar[s],
+                          ((dy * 3 + dx) * sp.cblocks + cb) * CB, n_tile * BN);
           }
-          const int ch = cb * 64;
+          const int ch = cb * CB;
           const bool second = ch >= g.C0;
           const uint8_t* sbase = second ? g.src1 : g.src0;
           const uint32_t rowoff = xo[2 * STRIP_ROWS + (second ? 4 : 0) + dy];
           const uint32_t* xcol = xo + (second ? STRIP_ROWS : 0);
           const uint32_t cc = static_cast<uint32_t>(second ? ch - g.C0 : ch) + c * 8;
 #pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            const int r = r0 + 32 * i;
+          for (int i = 0; i < (STRIP_PIX + ROWS_PER_PASS - 1) / ROWS_PER_PASS; ++i) {
+            const int r = r0 + ROWS_PER_PASS * i;
             if (r < STRIP_PIX) {
               const uint32_t xoff = xcol[r];
               const bool ok = (rowoff != 0xFFFFFFFFu) && (xoff != 0xFFFFFFFFu);
               const uint32_t off = ok ? rowoff + xoff + cc : 0u;
-              cp_async_16_zfill(stage + r * 128 + ((c ^ (r & 7)) << 4), sbase + static_cast<size_t>(off) * 2, ok);
+              // absolute-address swizzle: SW128: chunk ^ (row & 7); SW64: chunk ^ ((row >> 1) & 3)
+              const int sw = (CB == 64) ? (c ^ (r & 7)) : (c ^ ((r >> 1) & 3));
+              cp_async_16_zfill(stage + r * ROW_BYTES + (sw << 4), sbase + static_cast<size_t>(off) * 2, ok);
             }
           }
           cp_async_mbar_arrive_noinc(&full_bar[s]);
@@ -622,11 +633,11 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
           const uint32_t stage = smem_u32(stage0) + s * Cfg::STAGE_BYTES;
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
-            // the tap's A operand = the strip advanced by dx pixels (rows of 128 bytes)
-            const uint64_t a_desc = umma_smem_desc_sw128(stage + dx * 128, 16, 1024);
-            const uint64_t b_desc = umma_smem_desc_sw128(stage + STRIP_A_BYTES + dx * BN * 128, 16, 1024);
+            // the tap's A operand = the strip advanced by dx pixels (whole rows)
+            const uint64_t a_desc = umma_smem_desc(stage + dx * ROW_BYTES, 16, SBO, LAYOUT);
+            const uint64_t b_desc = umma_smem_desc(stage + Cfg::A_BYTES + dx * Cfg::B_TILE, 16, SBO, LAYOUT);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
+            for (int k = 0; k < CB / 16; ++k)
               umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (st | dx | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
@@ -698,11 +709,18 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
   }
 }
 
-template <int BN>
+// minimum fraction (percent) of the 128-pixel row segments that must be real output pixels (FP_STRIP_MINEFF)
+static int strip_min_eff() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FP_STRIP_MINEFF"); v = e ? atoi(e) : 80; }
+  return v;
+}
+
+template <int BN, int CB>
 static int launch_strip(const StripParams& sp, const CUtensorMap& tmap, cudaStream_t stream) {
-  using Cfg = StripCfg<BN>;
+  using Cfg = StripCfg<BN, CB>;
   static bool attr_set = false;
-  auto kern = conv_igemm_strip_kernel<BN>;
+  auto kern = conv_igemm_strip_kernel<BN, CB>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(strip smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -806,21 +824,36 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
   {
     const char* senv = getenv("FP_STRIP");
     const int segs = (d->wo + BM - 1) / BM;
-    const bool strip_ok = d->kh == 3 && d->kw == 3 && d->stride == 1 && d->up0 != 2 && (d->c0 % 64 == 0) && (d->c1 % 64 == 0) &&
-                          d->b_via_tma && d->bn <= 128 && d->bn >= 32 && d->kpad == 9 * (d->c0 + d->c1) &&
-                          d->wo * 5 >= segs * BM * 4 && !(senv && atoi(senv) == 0);
+    const int cb = (d->c0 % 64 == 0 && d->c1 % 64 == 0) ? 64 : ((d->c0 % 32 == 0 && d->c1 % 32 == 0) ? 32 : 0);
+    const bool strip_ok = d->kh == 3 && d->kw == 3 && d->stride == 1 && d->up0 != 2 && cb != 0 && d->b_via_tma &&
+                          d->bn <= 128 && d->bn >= 32 && (cb == 64 || d->bn <= 64) && d->kpad >= 9 * (d->c0 + d->c1) &&
+                          d->wo * 100 >= segs * BM * strip_min_eff() && !(senv && atoi(senv) == 0);
     if (strip_ok) {
       StripParams sp{};
       sp.b = p;
       sp.tiles_per_row = segs;
-      sp.cblocks = (d->c0 + d->c1) / 64;
+      sp.cblocks = (d->c0 + d->c1) / cb;
       sp.b.m_tiles = d->batch * d->ho * segs;
       sp.b.total_tiles = sp.b.m_tiles * sp.b.n_tiles;
-      switch (d->bn) {
-        case 32: return launch_strip<32>(sp, tmap, st);
-        case 64: return launch_strip<64>(sp, tmap, st);
-        case 128: return launch_strip<128>(sp, tmap, st);
-        default: break;
+      CUtensorMap tmap_s = tmap;
+      if (cb == 32) {     // 64-byte rows: weights tiles [bn][32] with SWIZZLE_64B
+        rc = make_tmap_2d(&tmap_s, w_packed, static_cast<uint64_t>(d->kpad), static_cast<uint64_t>(d->npad), 32u,
+                          static_cast<uint32_t>(d->bn), 64);
+        if (rc != FP_OK) return rc;
+      }
+      if (cb == 64) {
+        switch (d->bn) {
+          case 32: return launch_strip<32, 64>(sp, tmap_s, st);
+          case 64: return launch_strip<64, 64>(sp, tmap_s, st);
+          case 128: return launch_strip<128, 64>(sp, tmap_s, st);
+          default: break;
+        }
+      } else {
+        switch (d->bn) {
+          case 32: return launch_strip<32, 32>(sp, tmap_s, st);
+          case 64: return launch_strip<64, 32>(sp, tmap_s, st);
+          default: break;
+        }
       }
     }
   }

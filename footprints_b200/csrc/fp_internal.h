@@ -15,6 +15,9 @@ int num_sms();
 // 2-D row-major 16-bit matrix [rows][cols] -> tensor map with box {box_cols, box_rows}, SWIZZLE_128B.
 int make_tmap_2d_sw128(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
                        uint32_t box_rows);
+// same with an explicit swizzle span in bytes (128 or 64; box_cols * 2 must equal it)
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows,
+                 int swizzle_bytes);
 
 #define FP_CHECK_LAUNCH(name)                                                                  \
   do {                                                                                         \

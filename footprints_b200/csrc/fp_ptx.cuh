@@ -208,6 +208,18 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// generic form: layout 2 = SWIZZLE_128B (128-byte rows), 4 = SWIZZLE_64B (64-byte rows), 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint64_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= layout << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: fp32 accumulate, a/b formats 0 = f16, 1 = bf16.
 //   bits [4,6) c_format (1 = f32)   [7,10) a_format   [10,13) b_format
 //   bit 15 a_major (0 = K-major, 1 = MN-major)   bit 16 b_major   [17,23) N>>3   [24,29) M>>4

@@ -217,6 +217,10 @@ static const Case kCases[] = {
     {"strip_fullcorr_pad2_w322",     2, 64, 5, 320, 0, 0, 3, 1, 2, 0, 128, 128, 0, 1, 0, 1, 1, 1},
     {"strip_c128_bn32_zero_w640",    1, 128, 4, 640, 0, 0, 3, 1, 1, 0, 32, 32, 1, 0, 0, 0, 1, 1},
     {"strip_up_c64_bn32_w640",       2, 64, 3, 320, 1, 0, 3, 1, 1, 1, 32, 32, 2, 0, 0, 0, 0, 1},
+    // 32-channel rows -> SWIZZLE_64B strips
+    {"strip64B_c32_reflect_w640",    1, 32, 5, 640, 0, 0, 3, 1, 1, 1, 32, 32, 2, 0, 0, 0, 0, 1},
+    {"strip64B_c32_fullcorr_w322",   2, 32, 4, 320, 0, 0, 3, 1, 2, 0, 64, 64, 0, 1, 0, 1, 1, 1},
+    {"strip64B_c32_cat32_zero_w320", 1, 32, 6, 320, 0, 32, 3, 1, 1, 0, 32, 32, 1, 0, 0, 0, 1, 1},
 };
 static const Case kPerf[] = {
     {"perf_layer1_64x48x160_c64",    64, 64, 48, 160, 0, 0, 3, 1, 1, 0, 64, 64, 1, 0, 0, 1, 1, 1},
