@@ -56,6 +56,23 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t row
   return FP_OK;
 }
 
+// [rows][width][cols] 16-bit tensor (cols contiguous) -> box {box_cols, box_width, 1}, SWIZZLE_128B; out-of-range
+// width positions are zero-filled, which masks the overhang of 128-pixel row segments
+int make_tmap_3d_sw128(CUtensorMap* out, const void* base, uint64_t cols, uint64_t width, uint64_t rows, uint32_t box_cols,
+                       uint32_t box_width) {
+  auto enc = get_encode();
+  if (enc == nullptr) return set_error(FP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {cols, width, rows};
+  cuuint64_t strides[2] = {cols * 2, cols * width * 2};
+  cuuint32_t box[3] = {box_cols, box_width, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(FP_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d", static_cast<int>(r));
+  return FP_OK;
+}
+
 }  // namespace fp
 
 extern "C" int fp_version(void) { return FP_VERSION; }

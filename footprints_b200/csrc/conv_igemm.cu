@@ -743,10 +743,11 @@ static int ilog2_exact(int v) {
 
 using namespace fp;
 
-int fp::fill_gather_geom(const FpConvDesc* d, const void* src0, const void* src1, const char* who, GatherGeom& g) {
+int fp::fill_gather_geom(const FpConvDesc* d, const void* src0, const void* src1, const char* who, GatherGeom& g,
+                         bool need_pow2) {
   const int cin = d->c0 + d->c1;
   const int cl2 = ilog2_exact(cin);
-  if (cl2 < 3) return set_error(FP_ERR_ARG, "%s: c0+c1=%d must be a power of two >= 8", who, cin);
+  if (cl2 < 3 && (need_pow2 || cin < 8)) return set_error(FP_ERR_ARG, "%s: c0+c1=%d must be a power of two >= 8", who, cin);
   if ((d->c0 & 7) || (d->c1 & 7)) return set_error(FP_ERR_ARG, "%s: channel counts must be multiples of 8", who);
   if (d->c1 > 0 && src1 == nullptr) return set_error(FP_ERR_ARG, "%s: src1 is null but c1=%d", who, d->c1);
   if (d->kpad % 64 || d->kpad < d->kh * d->kw * cin) return set_error(FP_ERR_ARG, "%s: bad kpad %d", who, d->kpad);

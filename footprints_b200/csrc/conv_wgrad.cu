@@ -204,6 +204,299 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__
   }
 }
 
+// ==================================================================================================
+// Row-strip variant (3x3 stride-1 convolutions on wide rows; channel blocks of CB = 64 / 32 / 16): a pixel block is a
+// 128-pixel segment of one image row; for a filter row dy and a channel block the input row segment (130 pixels) is
+// staged once and the three horizontal taps are three MN-major B operands starting 0, 1, 2 rows into the strip (the
+// swizzle is a function of absolute shared-memory addresses, probe_umma_shift.cu).  Strip rows are CB*2 bytes
+// (SWIZZLE_128B / 64B / 32B).  A CTA owns (128 output channels) x (ndy filter rows) x (ncb channel blocks) x 3 taps x CB
+// TMEM columns for a range of row segments; dZ arrives by a 3-D TMA box whose out-of-row pixels are zero-filled.
+// ==================================================================================================
+constexpr int WS_STRIP_PIX = 130;
+constexpr int WS_STRIP_ROWS = 136;
+constexpr int WS_X_STAGES = 6;
+constexpr int WS_DZ_STAGES = 2;
+constexpr int WS_MAX_COLS = 384;                               // accumulator columns per CTA
+constexpr int WS_BAR_BYTES = 192;
+constexpr int WS_XOFF_WORDS = 2 * WS_STRIP_ROWS + 8;
+
+template <int CB> constexpr int ws_smem_bytes() {
+  return 1024 + WS_X_STAGES * WS_STRIP_ROWS * CB * 2 + WS_DZ_STAGES * WG_DZ_STAGE_BYTES + WS_BAR_BYTES + 16 +
+         2 * WS_XOFF_WORDS * 4;
+}
+
+struct WgradStripParams {
+  GatherGeom g;
+  int Cout, kpad, cin;
+  int tiles_per_row;          // ceil(Wo / 128)
+  int num_segments;           // batch * Ho * tiles_per_row
+  int cblocks, cb_per_unit, cb_groups;
+  int ndy, dy_groups;         // filter rows per CTA (3 or 1)
+  int co_tiles, splits, segs_per_split;
+  float* partial;
+  int a_fmt, b_fmt;
+  int fuse_taps;              // 1: one N = 3*CB instruction per K step (overlapping MN blocks)
+};
+
+template <int CB>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_strip_kernel(const __grid_constant__ WgradStripParams p, const __grid_constant__ CUtensorMap tmap_dz) {
+  constexpr int ROW_BYTES = CB * 2;
+  constexpr int STRIP_BYTES = WS_STRIP_ROWS * ROW_BYTES;        // multiple of 1024 for every CB
+  constexpr int CHUNKS = CB / 8;                                // 16-byte chunks per strip row
+  constexpr int ROWS_PER_PASS = WG_PRODUCER_THREADS / CHUNKS;
+  constexpr int PASSES = (WS_STRIP_PIX + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
+  constexpr uint32_t LAYOUT = CB == 64 ? 2u : (CB == 32 ? 4u : 6u);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* dz_tiles = smem;
+  uint8_t* x_tiles = smem + WS_DZ_STAGES * WG_DZ_STAGE_BYTES;
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(x_tiles + WS_X_STAGES * STRIP_BYTES);
+  uint64_t* x_empty = x_full + WS_X_STAGES;
+  uint64_t* dz_full = x_empty + WS_X_STAGES;
+  uint64_t* dz_empty = dz_full + WS_DZ_STAGES;
+  uint64_t* done_bar = dz_empty + WS_DZ_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(x_full) + WS_BAR_BYTES);
+  uint32_t* s_xoff = tmem_ptr_smem + 4;                         // [2][WS_XOFF_WORDS]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // unit -> (cb group, dy group, co tile, split)
+  int unit = blockIdx.x;
+  const int cbg = unit % p.cb_groups; unit /= p.cb_groups;
+  const int dy0 = (unit % p.dy_groups) * p.ndy; unit /= p.dy_groups;
+  const int co_tile = unit % p.co_tiles;
+  const int split = unit / p.co_tiles;
+  const int cb0 = cbg * p.cb_per_unit;
+  const int ncb = min(p.cb_per_unit, p.cblocks - cb0);
+  const int ndy = p.ndy;
+  const int seg_begin = split * p.segs_per_split;
+  const int seg_end = min(p.num_segments, seg_begin + p.segs_per_split);
+  const int nseg = max(seg_end - seg_begin, 0);
+  const bool two_halves = p.Cout - co_tile * 128 > 64;          // second 64-channel dZ block carries data
+  const GatherGeom& g = p.g;
+
+  if (tid == 0) {
+    for (int s = 0; s < WS_X_STAGES; ++s) {
+      mbar_init(&x_full[s], WG_PRODUCER_THREADS);
+      mbar_init(&x_empty[s], 1);
+    }
+    for (int s = 0; s < WS_DZ_STAGES; ++s) {
+      mbar_init(&dz_full[s], 1);
+      mbar_init(&dz_empty[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_dz);
+  }
+  if (warp == WG_MMA_WARP) tmem_alloc(tmem_ptr_smem, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < WG_PRODUCER_WARPS) {
+    // =============================== PRODUCERS ===============================
+    const int c = tid % CHUNKS, r0 = tid / CHUNKS;
+    const uint32_t x_u32 = smem_u32(x_tiles), dz_u32 = smem_u32(dz_tiles);
+    uint32_t xs = 0;
+    for (int i = 0; i < nseg; ++i) {
+      const int seg = seg_begin + i;
+      const int xseg = seg % p.tiles_per_row;
+      const int yrow = seg / p.tiles_per_row;            // b * Ho + y
+      const int img = yrow / g.Ho;
+      const int y = yrow - img * g.Ho;
+      const int x0 = xseg * 128;
+      uint32_t* xo = s_xoff + (i & 1) * WS_XOFF_WORDS;
+      if (tid < WS_STRIP_ROWS) {
+        int vx = x0 - g.pad_l + tid;
+        bool ok = tid < WS_STRIP_PIX;
+        if (g.pad_mode == FP_PAD_REFLECT) vx = vx < 0 ? -vx : (vx >= g.Win ? 2 * g.Win - 2 - vx : vx);
+        ok = ok && static_cast<unsigned>(vx) < static_cast<unsigned>(g.Win);
+        xo[tid] = ok ? static_cast<uint32_t>((g.up0 ? vx >> 1 : vx) * g.C0) : 0xFFFFFFFFu;
+        xo[WS_STRIP_ROWS + tid] = ok ? static_cast<uint32_t>(vx * g.C1) : 0xFFFFFFFFu;
+      } else if (tid < WS_STRIP_ROWS + 3) {
+        const int dy = tid - WS_STRIP_ROWS;
+        int vy = y - g.pad_t + dy;
+        if (g.pad_mode == FP_PAD_REFLECT) vy = vy < 0 ? -vy : (vy >= g.Hin ? 2 * g.Hin - 2 - vy : vy);
+        const bool ok = static_cast<unsigned>(vy) < static_cast<unsigned>(g.Hin);
+        xo[2 * WS_STRIP_ROWS + dy] = ok ? static_cast<uint32_t>(((img * g.H0 + (g.up0 ? vy >> 1 : vy)) * g.W0) * g.C0) : 0xFFFFFFFFu;
+        xo[2 * WS_STRIP_ROWS + 4 + dy] = ok ? static_cast<uint32_t>(((img * g.Hin + vy) * g.Win) * g.C1) : 0xFFFFFFFFu;
+      }
+      named_bar_sync(2, WG_PRODUCER_THREADS);
+      if (tid == 0) {
+        const int ds = i % WS_DZ_STAGES;
+        mbar_wait(&dz_empty[ds], ((i / WS_DZ_STAGES) & 1) ^ 1, 30);
+        mbar_arrive_expect_tx(&dz_full[ds], two_halves ? WG_DZ_STAGE_BYTES : WG_SUBTILE);
+        tma_load_3d(dz_u32 + ds * WG_DZ_STAGE_BYTES, &tmap_dz, &dz_full[ds], co_tile * 128, x0, yrow);
+        if (two_halves)
+          tma_load_3d(dz_u32 + ds * WG_DZ_STAGE_BYTES + WG_SUBTILE, &tmap_dz, &dz_full[ds], co_tile * 128 + 64, x0, yrow);
+      }
+      for (int dyi = 0; dyi < ndy; ++dyi)
+        for (int j = 0; j < ncb; ++j, ++xs) {
+          const int s = xs % WS_X_STAGES;
+          mbar_wait(&x_empty[s], ((xs / WS_X_STAGES) & 1) ^ 1, 31);
+          const uint32_t stage = x_u32 + s * STRIP_BYTES;
+          const int ch = (cb0 + j) * CB;
+          const bool second = ch >= g.C0;
+          const uint8_t* sbase = second ? g.src1 : g.src0;
+          const uint32_t rowoff = xo[2 * WS_STRIP_ROWS + (second ? 4 : 0) + dy0 + dyi];
+          const uint32_t* xcol = xo + (second ? WS_STRIP_ROWS : 0);
+          const uint32_t cc = static_cast<uint32_t>(second ? ch - g.C0 : ch) + c * 8;
+#pragma unroll
+          for (int k = 0; k < PASSES; ++k) {
+            const int r = r0 + ROWS_PER_PASS * k;
+            if (r < WS_STRIP_PIX) {
+              const uint32_t xoff = xcol[r];
+              const bool ok = (rowoff != 0xFFFFFFFFu) && (xoff != 0xFFFFFFFFu);
+              const uint32_t off = ok ? rowoff + xoff + cc : 0u;
+              const int sw = CB == 64 ? (r & 7) : (CB == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
+              cp_async_16_zfill(stage + r * ROW_BYTES + ((c ^ sw) << 4), sbase + static_cast<size_t>(off) * 2, ok);
+            }
+          }
+          cp_async_mbar_arrive_noinc(&x_full[s]);
+        }
+    }
+  } else if (warp == WG_MMA_WARP) {
+    // =============================== MMA ISSUER ===============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(128, CB, p.a_fmt, p.b_fmt, 1, 1);
+      const uint32_t idesc3 = umma_idesc_f16(128, 3 * CB, p.a_fmt, p.b_fmt, 1, 1);
+      uint32_t xs = 0;
+      for (int i = 0; i < nseg; ++i) {
+        const int ds = i % WS_DZ_STAGES;
+        mbar_wait(&dz_full[ds], (i / WS_DZ_STAGES) & 1, 32);
+        const uint32_t a_base = smem_u32(dz_tiles) + ds * WG_DZ_STAGE_BYTES;
+        for (int dyi = 0; dyi < ndy; ++dyi)
+          for (int j = 0; j < ncb; ++j, ++xs) {
+            const int s = xs % WS_X_STAGES;
+            mbar_wait(&x_full[s], (xs / WS_X_STAGES) & 1, 33);
+            tcgen05_fence_after();
+            const uint32_t strip = smem_u32(x_tiles) + s * STRIP_BYTES;
+            const uint32_t d_tmem = tmem_base + ((dyi * ncb + j) * 3) * CB;
+            if (p.fuse_taps) {
+              // one N = 3*CB instruction per K step: B's three MN blocks are the strip at pixel shifts 0, 1, 2 (block
+              // stride LBO = one strip row), so dZ (the A operand) is read from shared memory once instead of 3 times
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t a_desc = umma_smem_desc_sw128(a_base + ks * 2048, WG_SUBTILE, 1024);
+                const uint64_t b_desc = umma_smem_desc(strip + ks * 16 * ROW_BYTES, ROW_BYTES, 8 * ROW_BYTES, LAYOUT);
+                umma_f16(d_tmem, a_desc, b_desc, idesc3, (i | ks) != 0 ? 1u : 0u);
+              }
+            } else {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                  const uint64_t a_desc = umma_smem_desc_sw128(a_base + ks * 2048, WG_SUBTILE, 1024);
+                  // B = the strip advanced by dx pixels (rows); N = CB channels = one MN block (LBO unused)
+                  const uint64_t b_desc = umma_smem_desc(strip + dx * ROW_BYTES + ks * 16 * ROW_BYTES, 8 * ROW_BYTES,
+                                                         8 * ROW_BYTES, LAYOUT);
+                  umma_f16(d_tmem + dx * CB, a_desc, b_desc, idesc, (i | ks) != 0 ? 1u : 0u);
+                }
+              }
+            }
+            umma_commit(&x_empty[s]);
+          }
+        umma_commit(&dz_empty[ds]);
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else {
+    // =============================== EPILOGUE (once) ===============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait<256>(done_bar, 0, 34);
+    tcgen05_fence_after();
+    const bool row_ok = co_tile * 128 + row < p.Cout;
+    float* dst_row = p.partial + (static_cast<size_t>(split) * p.co_tiles * 128 + co_tile * 128 + row) * p.kpad;
+    if (co_tile * 128 + q * 32 < p.Cout)                       // warp-uniform: this quarter holds real output channels
+      for (int dyi = 0; dyi < ndy; ++dyi)
+        for (int j = 0; j < ncb; ++j)
+          for (int dx = 0; dx < 3; ++dx) {
+            float* dst = dst_row + ((dy0 + dyi) * 3 + dx) * p.cin + (cb0 + j) * CB;
+#pragma unroll 1
+            for (int cidx = 0; cidx < CB; cidx += 16) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(tmem_base + ((dyi * ncb + j) * 3 + dx) * CB + cidx + (static_cast<uint32_t>(q * 32) << 16), v);
+              tmem_ld_wait();
+              if (row_ok) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                  *reinterpret_cast<float4*>(dst + cidx + 4 * x) =
+                      nseg > 0 ? make_float4(__uint_as_float(v[4 * x]), __uint_as_float(v[4 * x + 1]),
+                                             __uint_as_float(v[4 * x + 2]), __uint_as_float(v[4 * x + 3]))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+          }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == WG_MMA_WARP) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+struct WgradStripPlan {
+  int cb, tiles_per_row, num_segments, cblocks, cb_per_unit, cb_groups, ndy, dy_groups, co_tiles, splits, segs_per_split;
+};
+
+static int wgrad_strip_cb(const FpConvDesc* d) {
+  const int c0 = d->c0, c1 = d->c1;
+  if (c0 % 64 == 0 && c1 % 64 == 0) return 64;
+  if (c0 % 32 == 0 && c1 % 32 == 0) return 32;
+  if (c0 % 16 == 0 && c1 % 16 == 0) return 16;
+  return 0;
+}
+
+static bool wgrad_strip_ok(const FpConvDesc* d) {
+  const char* senv = getenv("FP_WGRAD_STRIP");
+  const int segs = (d->wo + 127) / 128;
+  const int cb = wgrad_strip_cb(d);
+  const int cin = d->c0 + d->c1;
+  return d->kh == 3 && d->kw == 3 && d->stride == 1 && d->up0 != 2 && cb != 0 && d->kpad >= 9 * cin &&
+         (cb == 64 || cin / cb <= 2) && d->wo * 100 >= segs * 128 * 80 && !(senv && atoi(senv) == 0);
+}
+
+static WgradStripPlan wgrad_strip_plan(const FpConvDesc* d) {
+  WgradStripPlan w;
+  w.cb = wgrad_strip_cb(d);
+  w.tiles_per_row = (d->wo + 127) / 128;
+  w.num_segments = d->batch * d->ho * w.tiles_per_row;
+  w.cblocks = (d->c0 + d->c1) / w.cb;
+  const int max_cb = WS_MAX_COLS / (3 * w.cb);               // channel blocks whose 3 taps fit the accumulator budget
+  w.cb_groups = (w.cblocks + max_cb - 1) / max_cb;
+  w.cb_per_unit = (w.cblocks + w.cb_groups - 1) / w.cb_groups;
+  w.cb_groups = (w.cblocks + w.cb_per_unit - 1) / w.cb_per_unit;
+  w.ndy = 9 * w.cb * w.cb_per_unit <= WS_MAX_COLS ? 3 : 1;
+  w.dy_groups = 3 / w.ndy;
+  w.co_tiles = (d->cout + 127) / 128;
+  const int base = w.cb_groups * w.dy_groups * w.co_tiles;
+  int want = num_sms() / base;                                 // one resident CTA per SM: a single full wave
+  if (want < 1) want = 1;
+  if (want > w.num_segments) want = w.num_segments;
+  w.segs_per_split = (w.num_segments + want - 1) / want;
+  w.splits = (w.num_segments + w.segs_per_split - 1) / w.segs_per_split;
+  return w;
+}
+
+template <int CB>
+static int launch_wgrad_strip(const WgradStripParams& sp, const CUtensorMap& tm, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_strip_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ws_smem_bytes<CB>());
+    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(wgrad strip): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  conv_wgrad_strip_kernel<CB><<<grid, WG_THREADS, ws_smem_bytes<CB>(), st>>>(sp, tm);
+  FP_CHECK_LAUNCH("fp_conv_wgrad(strip)");
+  return FP_OK;
+}
+
 // dW_oihw[co][ci][ky][kx] (+)= sum over splits of partial[split][co][(ky*kw+kx)*cin + ci]; stem = 1 inverts the
 // space-to-depth packing of fp_pack_stem_weight.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int co_rows, int kpad, int cout,
@@ -267,6 +560,10 @@ using namespace fp;
 
 extern "C" long long fp_conv_wgrad_workspace_bytes(const FpConvDesc* d) {
   if (d == nullptr) return -1;
+  if (wgrad_strip_ok(d)) {
+    const WgradStripPlan ws = wgrad_strip_plan(d);
+    return static_cast<long long>(ws.splits) * ws.co_tiles * 128 * d->kpad * 4;
+  }
   const WgradPlan w = wgrad_plan(d);
   return static_cast<long long>(w.splits) * w.co_tiles * 128 * d->kpad * 4;
 }
@@ -275,11 +572,41 @@ extern "C" int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* 
                              int grad_dtype, int stem, int accumulate, float* dw_oihw, float* workspace, void* stream) {
   if (!d || !src0 || !dz || !dw_oihw || !workspace) return set_error(FP_ERR_ARG, "fp_conv_wgrad: null argument");
   WgradParams p{};
-  int rc = fill_gather_geom(d, src0, src1, "fp_conv_wgrad", p.g);
+  int rc = fill_gather_geom(d, src0, src1, "fp_conv_wgrad", p.g, stem || !wgrad_strip_ok(d));
   if (rc != FP_OK) return rc;
   if (dz_ld < d->cout || (dz_ld & 7)) return set_error(FP_ERR_ARG, "fp_conv_wgrad: dz_ld=%d must be a multiple of 8 >= cout", dz_ld);
   rc = fp_check_device();
   if (rc != FP_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cin_r = stem ? 3 : d->c0 + d->c1;
+  const int kh_r = stem ? 7 : d->kh, kw_r = stem ? 7 : d->kw;
+  if (!stem && wgrad_strip_ok(d)) {
+    WgradStripParams sp{};
+    sp.g = p.g;
+    const WgradStripPlan ws = wgrad_strip_plan(d);
+    sp.Cout = d->cout; sp.kpad = d->kpad; sp.cin = d->c0 + d->c1;
+    sp.tiles_per_row = ws.tiles_per_row; sp.num_segments = ws.num_segments; sp.cblocks = ws.cblocks;
+    sp.cb_per_unit = ws.cb_per_unit; sp.cb_groups = ws.cb_groups; sp.ndy = ws.ndy; sp.dy_groups = ws.dy_groups;
+    sp.co_tiles = ws.co_tiles; sp.splits = ws.splits; sp.segs_per_split = ws.segs_per_split;
+    sp.partial = workspace; sp.a_fmt = grad_dtype; sp.b_fmt = d->dtype;
+    {
+      const char* fenv = getenv("FP_WGRAD_FUSE_TAPS");
+      sp.fuse_taps = fenv ? atoi(fenv) : 1;
+    }
+    CUtensorMap tmap_dz3;
+    rc = make_tmap_3d_sw128(&tmap_dz3, dz, static_cast<uint64_t>(dz_ld), static_cast<uint64_t>(d->wo),
+                            static_cast<uint64_t>(d->batch) * d->ho, 64u, 128u);
+    if (rc != FP_OK) return rc;
+    const int grid_s = ws.cb_groups * ws.dy_groups * ws.co_tiles * ws.splits;
+    rc = ws.cb == 64 ? launch_wgrad_strip<64>(sp, tmap_dz3, grid_s, st)
+                     : (ws.cb == 32 ? launch_wgrad_strip<32>(sp, tmap_dz3, grid_s, st) : launch_wgrad_strip<16>(sp, tmap_dz3, grid_s, st));
+    if (rc != FP_OK) return rc;
+    const long long total_s = static_cast<long long>(d->cout) * d->kpad;
+    wgrad_reduce_kernel<<<static_cast<unsigned>((total_s + 255) / 256), 256, 0, st>>>(
+        workspace, ws.splits, ws.co_tiles * 128, d->kpad, d->cout, cin_r, d->c0 + d->c1, kh_r, kw_r, 0, accumulate, dw_oihw);
+    FP_CHECK_LAUNCH("fp_conv_wgrad(strip reduce)");
+    return FP_OK;
+  }
   p.dz_ld = dz_ld; p.Cout = d->cout; p.kpad = d->kpad;
   const WgradPlan w = wgrad_plan(d);
   p.k_chunks = w.k_chunks; p.chunks_per_group = w.chunks_per_group; p.k_groups = w.k_groups;
@@ -292,7 +619,6 @@ extern "C" int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* 
     if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = p.k_groups * p.co_tiles * p.splits;
   CUtensorMap tmap_dz;
   rc = make_tmap_2d_sw128(&tmap_dz, dz, static_cast<uint64_t>(dz_ld), static_cast<uint64_t>(p.g.M), 64u, 128u);

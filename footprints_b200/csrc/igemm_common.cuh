@@ -117,6 +117,8 @@ __device__ __forceinline__ int gather_row_index(const KDecode& k, const uint4& r
 }
 
 // host: validate an FpConvDesc's gather part and fill the geometry
-int fill_gather_geom(const FpConvDesc* d, const void* src0, const void* src1, const char* who, GatherGeom& g);
+// need_pow2 = false: callers that never decode k -> (tap, channel) by shifts (the row-strip kernels) accept any c0+c1
+int fill_gather_geom(const FpConvDesc* d, const void* src0, const void* src1, const char* who, GatherGeom& g,
+                     bool need_pow2 = true);
 
 }  // namespace fp

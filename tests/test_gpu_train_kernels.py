@@ -168,11 +168,19 @@ def _fwd_desc(b, c0, h0, w0, up0, c1, k, stride, pad, pad_mode, cout):
     dict(c0=32, c1=32, up0=1, k=3, stride=1, pad=1, pad_mode=1, cout=32),
     dict(c0=256, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=0, cout=256),
     dict(c0=64, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=1, cout=2),
+    # wide rows -> row-strip kernels (forward/dgrad and wgrad): 1.x segments per row, ragged tail, concat, upsample
+    dict(c0=64, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=0, cout=64, w0=160, h0=6, b=2),
+    dict(c0=64, c1=64, up0=1, k=3, stride=1, pad=1, pad_mode=1, cout=64, w0=80, h0=4, b=2),
+    dict(c0=128, c1=64, up0=1, k=3, stride=1, pad=1, pad_mode=1, cout=256, w0=60, h0=3, b=2),
+    dict(c0=192, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=1, cout=32, w0=250, h0=3, b=1),
+    dict(c0=32, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=1, cout=32, w0=160, h0=6, b=2),      # 64-byte strip rows
+    dict(c0=32, c1=32, up0=1, k=3, stride=1, pad=1, pad_mode=1, cout=2, w0=80, h0=4, b=2),
+    dict(c0=16, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=0, cout=16, w0=130, h0=5, b=2),      # 32-byte strip rows
 ])
 def test_conv_wgrad_and_dgrad(lib, cfg):
     """Weight gradient (fp_conv_wgrad) and data gradient (fp_conv_fwd with the rotated filter) against autograd."""
     g = torch.Generator().manual_seed(5)
-    b, h0, w0 = 3, 10, 14
+    b, h0, w0 = cfg.get('b', 3), cfg.get('h0', 10), cfg.get('w0', 14)
     d, hin, win = _fwd_desc(b, cfg['c0'], h0, w0, cfg['up0'], cfg['c1'], cfg['k'], cfg['stride'], cfg['pad'],
                             cfg['pad_mode'], cfg['cout'])
     cin, cout, k = cfg['c0'] + cfg['c1'], cfg['cout'], cfg['k']
