@@ -136,6 +136,91 @@ head_fwd_pixel_kernel(const uint4* __restrict__ x, const float* __restrict__ w, 
   out[idx] = make_float2(a0, a1);
 }
 
+// Shared-memory tiled forward (the default): a block of 128 threads owns a 16 x 32 tile of output pixels and walks the
+// channels in chunks of 32.  Per chunk the (16+2) x (32+2) reflected halo tile is staged once (coalesced 16-byte
+// loads; 80-byte pixel stride = 64 data + 16 pad bytes, so that the 32 lanes of a warp -- consecutive pixels -- hit all
+// banks on 16-byte reads), then each thread produces 4 vertically adjacent pixels: for every (8-channel group, dx) it
+// reads 6 input rows once and applies the three dy taps from registers, so a weight pair fetched from shared memory is
+// used for 4 pixels and an input value for up to 3 -- FMA-bound instead of L1-wavefront-bound (the per-pixel kernels
+// above issue 16 wavefronts per 64-byte-strided global load).
+constexpr int HT_ROWS = 16, HT_COLS = 32, HT_THREADS = 128, HT_CB = 32;
+constexpr int HT_PIX_BYTES = HT_CB * 2 + 16;
+constexpr int HT_HALO_PIX = (HT_ROWS + 2) * (HT_COLS + 2);
+constexpr int HT_SMEM_BYTES = HT_HALO_PIX * HT_PIX_BYTES + 9 * HT_CB * static_cast<int>(sizeof(float2));
+
+__global__ void __launch_bounds__(HT_THREADS)
+head_fwd_tile_kernel(const uint4* __restrict__ x, const float* __restrict__ w /*[2][C][3][3]*/,
+                     const float* __restrict__ bias, int H, int W, int C, int tiles_x, int tiles_y, int sigmoid, int fmt,
+                     float2* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t ht_smem[];
+  uint8_t* tile = ht_smem;
+  float2* sw = reinterpret_cast<float2*>(ht_smem + HT_HALO_PIX * HT_PIX_BYTES);     // [tap][32]
+  const int tid = threadIdx.x;
+  int bid = blockIdx.x;
+  const int tx0 = (bid % tiles_x) * HT_COLS; bid /= tiles_x;
+  const int ty0 = (bid % tiles_y) * HT_ROWS;
+  const long long img = bid / tiles_y;
+  const int c8 = C >> 3;
+  const int lx = tid & 31, ly = (tid >> 5) * 4;          // this thread: column lx, rows ly .. ly+3 of the tile
+  float acc[4][2];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
+
+  for (int cb = 0; cb < C; cb += HT_CB) {
+    const int nch = min(HT_CB, C - cb);                  // 8, 16, 24 or 32 channels in this chunk
+    const int nq = nch >> 3;
+    __syncthreads();                                     // previous chunk fully consumed
+    for (int i = tid; i < HT_HALO_PIX * nq; i += HT_THREADS) {
+      const int pix = i / nq, q = i - pix * nq;
+      const int hy = pix / (HT_COLS + 2), hx = pix - hy * (HT_COLS + 2);
+      int yy = reflect1(ty0 + hy - 1, H), xx = reflect1(tx0 + hx - 1, W);
+      yy = min(max(yy, 0), H - 1); xx = min(max(xx, 0), W - 1);   // rows / columns past a ragged tile: any valid pixel
+      *reinterpret_cast<uint4*>(tile + pix * HT_PIX_BYTES + q * 16) = __ldg(&x[((img * H + yy) * W + xx) * c8 + (cb >> 3) + q]);
+    }
+    for (int i = tid; i < 9 * nch; i += HT_THREADS) {
+      const int t = i / nch, c = i - t * nch;
+      sw[t * HT_CB + c] = make_float2(w[(0 * C + cb + c) * 9 + t], w[(1 * C + cb + c) * 9 + t]);
+    }
+    __syncthreads();
+    for (int q = 0; q < nq; ++q) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        float f[6][8];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+          h_unpack8(*reinterpret_cast<const uint4*>(tile + ((ly + r) * (HT_COLS + 2) + lx + dx) * HT_PIX_BYTES + q * 16), fmt, f[r]);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const float2* wt = sw + (dy * 3 + dx) * HT_CB + q * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 ww = wt[i];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              acc[r][0] = fmaf(f[r + dy][i], ww.x, acc[r][0]);
+              acc[r][1] = fmaf(f[r + dy][i], ww.y, acc[r][1]);
+            }
+          }
+        }
+      }
+    }
+  }
+  const float b0 = bias[0], b1 = bias[1];
+  const int px = tx0 + lx;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int py = ty0 + ly + r;
+    if (py < H && px < W) {
+      float a0 = acc[r][0] + b0, a1 = acc[r][1] + b1;
+      if (sigmoid) {
+        a0 = 1.f / (1.f + expf(-a0));
+        a1 = 1.f / (1.f + expf(-a1));
+      }
+      out[(img * H + py) * W + px] = make_float2(a0, a1);
+    }
+  }
+}
+
 // Same idea for the data gradient at C == 32: one thread per pixel owns all 32 channels, so each dZ value is loaded
 // once per tap instead of once per chunk.
 __global__ void __launch_bounds__(HEAD_THREADS)
@@ -276,6 +361,112 @@ head_dgrad_kernel(const uint4* __restrict__ dz8 /*[B][H][W][8] 16-bit, ch 0..1 v
   dst[idx] = o;
 }
 
+// Shared-memory tiled data gradient (the default for C % 16 == 0): a block of 128 threads owns a 16 x 32 pixel tile.
+// Stage 1 builds G[tap][pixel] = sum of dZ over the virtual positions that reflect onto the pixel (the adjoint of the
+// reflection padding, 1 / 2 / 4 terms) once per tile; stage 2 is a plain FMA loop dX[p][c] = sum_tap G[tap][p] . W[.][c][tap]
+// with every thread producing 4 pixels x 16 channels per pass (weight pairs broadcast from shared memory are used for 4
+// pixels, G values for 16 channels) and writing whole 32-byte sectors.
+constexpr int HD_SMEM_G = 9 * HT_ROWS * HT_COLS * static_cast<int>(sizeof(float2));     // 36 KB
+
+__global__ void __launch_bounds__(HT_THREADS)
+head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ w, int H, int W, int C, int tiles_x,
+                       int tiles_y, int accumulate, const uint4* __restrict__ yact, int act, int act_fmt, int grad_fmt,
+                       uint4* __restrict__ dst) {
+  extern __shared__ __align__(16) uint8_t hd_smem[];
+  float2* G = reinterpret_cast<float2*>(hd_smem);                       // [9][16*32]
+  float2* sw = reinterpret_cast<float2*>(hd_smem + HD_SMEM_G);          // [9][C]
+  const int tid = threadIdx.x;
+  int bid = blockIdx.x;
+  const int tx0 = (bid % tiles_x) * HT_COLS; bid /= tiles_x;
+  const int ty0 = (bid % tiles_y) * HT_ROWS;
+  const long long img = bid / tiles_y;
+  const int c8 = C >> 3;
+  for (int i = tid; i < 9 * C; i += HT_THREADS) {
+    const int t = i / C, c = i - t * C;
+    sw[i] = make_float2(w[(0 * C + c) * 9 + t], w[(1 * C + c) * 9 + t]);
+  }
+  for (int i = tid; i < 9 * HT_ROWS * HT_COLS; i += HT_THREADS) {
+    const int t = i / (HT_ROWS * HT_COLS), pix = i - t * (HT_ROWS * HT_COLS);
+    const int py = ty0 + pix / HT_COLS, px = tx0 + (pix % HT_COLS);
+    const int tyy = t / 3, txx = t - tyy * 3;
+    float2 g = make_float2(0.f, 0.f);
+    if (py < H && px < W) {
+      // virtual rows / columns (in [-1, H] x [-1, W]) that reflect onto (py, px)
+      int vy[3], vx[3], ny = 1, nx = 1;
+      vy[0] = py; vx[0] = px;
+      if (py == 1) vy[ny++] = -1;
+      if (py == H - 2) vy[ny++] = H;
+      if (px == 1) vx[nx++] = -1;
+      if (px == W - 2) vx[nx++] = W;
+      for (int iy = 0; iy < ny; ++iy) {
+        const int qy = vy[iy] - tyy + 1;
+        if (qy < 0 || qy >= H) continue;
+        for (int ix = 0; ix < nx; ++ix) {
+          const int qx = vx[ix] - txx + 1;
+          if (qx < 0 || qx >= W) continue;
+          const float2 d = h_up2(__ldg(reinterpret_cast<const uint32_t*>(dz8 + (img * H + qy) * W + qx)), grad_fmt);
+          g.x += d.x; g.y += d.y;
+        }
+      }
+    }
+    G[i] = g;
+  }
+  __syncthreads();
+  const int lx = tid & 31, ly = (tid >> 5) * 4;
+  const int px = tx0 + lx;
+  for (int cb = 0; cb < C; cb += 16) {
+    float acc[4][16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[r][i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float2 g[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) g[r] = G[t * (HT_ROWS * HT_COLS) + (ly + r) * HT_COLS + lx];
+      const float2* wt = sw + t * C + cb;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 ww = wt[i];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r][i] = fmaf(ww.x, g[r].x, fmaf(ww.y, g[r].y, acc[r][i]));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int py = ty0 + ly + r;
+      if (py >= H || px >= W) continue;
+      const long long o = ((img * H + py) * W + px) * c8 + (cb >> 3);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = acc[r][h * 8 + i];
+        if (accumulate) {
+          float f[8];
+          h_unpack8(dst[o + h], grad_fmt, f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] += f[i];
+        }
+        if (yact != nullptr) {
+          float fy[8];
+          h_unpack8(__ldg(&yact[o + h]), act_fmt, fy);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (act == FP_ACT_ELU) a[i] *= fy[i] > 0.f ? 1.f : fy[i] + 1.f;
+            else if (act == FP_ACT_RELU) a[i] = fy[i] > 0.f ? a[i] : 0.f;
+          }
+        }
+        uint4 v;
+        v.x = h_pk2(a[0], a[1], grad_fmt); v.y = h_pk2(a[2], a[3], grad_fmt);
+        v.z = h_pk2(a[4], a[5], grad_fmt); v.w = h_pk2(a[6], a[7], grad_fmt);
+        dst[o + h] = v;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- weight gradient
 // Stage 1: block b reduces its pixel range; thread = (pixel sub-range g, tap t, 8-channel chunk cc) accumulates
 // 2 x 8 sums, then a fixed-order shared-memory reduction over g.  partial[b][co][c][t] (+ bias sums at the end).
@@ -376,7 +567,18 @@ extern "C" int fp_head_conv_fwd(const void* x, const float* w_oihw, const float*
   int rc = head_check("fp_head_conv_fwd", c, h, w);
   if (rc != FP_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (c <= 32) {
+  const char* tenv = getenv("FP_HEAD_TILE");
+  if (!(tenv && atoi(tenv) == 0)) {
+    const int tiles_x = (w + HT_COLS - 1) / HT_COLS, tiles_y = (h + HT_ROWS - 1) / HT_ROWS;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(head_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES);
+      if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(head fwd): %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    head_fwd_tile_kernel<<<static_cast<unsigned>(static_cast<long long>(batch) * tiles_x * tiles_y), HT_THREADS, HT_SMEM_BYTES, st>>>(
+        static_cast<const uint4*>(x), w_oihw, bias, h, w, c, tiles_x, tiles_y, sigmoid, dtype, reinterpret_cast<float2*>(out));
+  } else if (c <= 32) {
     const long long n = static_cast<long long>(batch) * h * w;             // one thread per pixel
     head_fwd_pixel_kernel<<<static_cast<unsigned>((n + HEAD_THREADS - 1) / HEAD_THREADS), HEAD_THREADS, 0, st>>>(
         static_cast<const uint4*>(x), w_oihw, bias, batch, h, w, c, sigmoid, dtype, reinterpret_cast<float2*>(out));
@@ -395,7 +597,21 @@ extern "C" int fp_head_conv_dgrad(const void* dz8, const float* w_oihw, int batc
   int rc = head_check("fp_head_conv_dgrad", c, h, w);
   if (rc != FP_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (c == 32) {
+  const char* tenv = getenv("FP_HEAD_TILE");
+  if (c % 16 == 0 && !(tenv && atoi(tenv) == 0)) {
+    const int tiles_x = (w + HT_COLS - 1) / HT_COLS, tiles_y = (h + HT_ROWS - 1) / HT_ROWS;
+    const int smem = HD_SMEM_G + 9 * c * static_cast<int>(sizeof(float2));
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(head_dgrad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           HD_SMEM_G + 9 * HEAD_MAX_C * static_cast<int>(sizeof(float2)));
+      if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(head dgrad): %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    head_dgrad_tile_kernel<<<static_cast<unsigned>(static_cast<long long>(batch) * tiles_x * tiles_y), HT_THREADS, smem, st>>>(
+        static_cast<const uint4*>(dz8), w_oihw, h, w, c, tiles_x, tiles_y, accumulate, static_cast<const uint4*>(y_act), act,
+        act_dtype, grad_dtype, static_cast<uint4*>(dst));
+  } else if (c == 32) {
     const long long n = static_cast<long long>(batch) * h * w;
     head_dgrad_pixel32_kernel<<<static_cast<unsigned>((n + HEAD_THREADS - 1) / HEAD_THREADS), HEAD_THREADS, 0, st>>>(
         static_cast<const uint4*>(dz8), w_oihw, batch, h, w, accumulate, static_cast<const uint4*>(y_act), act, act_dtype,

@@ -45,7 +45,7 @@ constexpr int RED_MAX_BLOCKS = 592;   // 4 x 148 SMs
 // partial layout: [block][2][C] fp32.  Each thread owns one 8-channel chunk and strides over rows.
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(RED_THREADS)
+__global__ void __launch_bounds__(RED_THREADS, MODE == 1 ? 3 : 4)   // mode 1 holds two rows of three tensors in flight
 col_reduce_kernel(const uint4* __restrict__ a, int a_fmt, const uint4* __restrict__ y, const uint4* __restrict__ z,
                   int act_fmt, const float* __restrict__ mean, const float* __restrict__ invstd, long long M, int C,
                   float* __restrict__ partial) {
@@ -62,17 +62,19 @@ col_reduce_kernel(const uint4* __restrict__ a, int a_fmt, const uint4* __restric
     for (int i = 0; i < 8; ++i) { mu[i] = mean[tx * 8 + i]; is[i] = invstd[tx * 8 + i]; }
   }
   if (ty < rows_per_pass) {
-    for (long long r = static_cast<long long>(blockIdx.x) * rows_per_pass + ty; r < M;
-         r += static_cast<long long>(gridDim.x) * rows_per_pass) {
+    // two rows per iteration: twice the loads in flight per thread (the reductions are latency-, not bandwidth-limited
+    // at 4 blocks x 256 threads per SM otherwise)
+    const long long step = static_cast<long long>(gridDim.x) * rows_per_pass;
+    auto accumulate_row = [&](const uint4& va, const uint4& vy, const uint4& vz) {
       float f[8];
-      unpack8(a[r * c8 + tx], a_fmt, f);
+      unpack8(va, a_fmt, f);
       if (MODE == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s0[i] += f[i]; s1[i] += f[i] * f[i]; }
       } else if (MODE == 1) {
         float fy[8], fz[8];
-        if (y != nullptr) unpack8(y[r * c8 + tx], act_fmt, fy);   // y == nullptr: no ReLU follows this BatchNorm
-        unpack8(z[r * c8 + tx], act_fmt, fz);
+        if (y != nullptr) unpack8(vy, act_fmt, fy);   // y == nullptr: no ReLU follows this BatchNorm
+        unpack8(vz, act_fmt, fz);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float g = (y == nullptr || fy[i] > 0.f) ? f[i] : 0.f;
@@ -83,6 +85,28 @@ col_reduce_kernel(const uint4* __restrict__ a, int a_fmt, const uint4* __restric
 #pragma unroll
         for (int i = 0; i < 8; ++i) s0[i] += f[i];
       }
+    };
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    long long r = static_cast<long long>(blockIdx.x) * rows_per_pass + ty;
+    for (; r + step < M; r += 2 * step) {
+      const long long i0 = r * c8 + tx, i1 = (r + step) * c8 + tx;
+      const uint4 a0 = a[i0], a1 = a[i1];
+      uint4 y0 = zero4, y1 = zero4, z0 = zero4, z1 = zero4;
+      if (MODE == 1) {
+        if (y != nullptr) { y0 = y[i0]; y1 = y[i1]; }
+        z0 = z[i0]; z1 = z[i1];
+      }
+      accumulate_row(a0, y0, z0);
+      accumulate_row(a1, y1, z1);
+    }
+    if (r < M) {
+      const long long i0 = r * c8 + tx;
+      uint4 y0 = zero4, z0 = zero4;
+      if (MODE == 1) {
+        if (y != nullptr) y0 = y[i0];
+        z0 = z[i0];
+      }
+      accumulate_row(a[i0], y0, z0);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -448,56 +472,80 @@ __global__ void grad_add_kernel(uint4* __restrict__ a, const uint4* __restrict__
   a[idx] = pack8(fa, grad_fmt);
 }
 
-// max-pool 3x3/2 pad 1 backward: every input pixel gathers from the (<= 4) windows that contain it and takes
-// the gradient of those whose maximum it is (first maximum in scan order wins ties, like ATen).
-template <typename V>
-__global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, int batch, int h, int w,
-                                   int c8, int act_fmt, int grad_fmt, int accumulate, uint4* __restrict__ dx) {
-  const int ho = (h + 1) / 2, wo = (w + 1) / 2;
+// max-pool 3x3/2 pad 1 backward (h, w even): one thread per 2x2 block of input pixels and 8-channel chunk.  The block
+// is covered by the four windows (oy, ox) in {j, j+1} x {i, i+1}; each window's argmax (first maximum in scan order
+// wins ties, like ATen) is found once and its gradient routed to whichever of the four pixels holds it -- a gather,
+// so the result is deterministic and every dx element is written exactly once.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, int batch, int h, int w, int c8,
+                   int act_fmt, int grad_fmt, int accumulate, uint4* __restrict__ dx) {
+  const int ho = h / 2, wo = w / 2;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (idx >= static_cast<long long>(batch) * h * w * c8) return;
+  if (idx >= static_cast<long long>(batch) * ho * wo * c8) return;
   const int cc = static_cast<int>(idx % c8);
   long long t = idx / c8;
-  const int ix = static_cast<int>(t % w); t /= w;
-  const int iy = static_cast<int>(t % h);
-  const int b = static_cast<int>(t / h);
-  float xin[8], acc[8];
-  unpack8(x[idx], act_fmt, xin);
+  const int i = static_cast<int>(t % wo); t /= wo;
+  const int j = static_cast<int>(t % ho);
+  const long long b = t / ho;
+  float acc[4][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int oy = max(0, (iy - 1 + 1) / 2); oy <= min(ho - 1, (iy + 1) / 2); ++oy)
-    for (int ox = max(0, (ix - 1 + 1) / 2); ox <= min(wo - 1, (ix + 1) / 2); ++ox) {
-      // argmax of window (oy, ox) in scan order
-      float best[8]; int by[8], bx[8];
+  for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; by[i] = -1; bx[i] = -1; }
-      for (int dy_ = -1; dy_ <= 1; ++dy_) {
-        const int yy = 2 * oy + dy_;
+    for (int e = 0; e < 8; ++e) acc[q][e] = 0.f;
+#pragma unroll
+  for (int wy = 0; wy < 2; ++wy) {
+    const int oy = j + wy;
+    if (oy >= ho) continue;
+#pragma unroll
+    for (int wx = 0; wx < 2; ++wx) {
+      const int ox = i + wx;
+      if (ox >= wo) continue;
+      float best[8]; int pos[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; pos[e] = -1; }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = 2 * oy + ky - 1;
         if (yy < 0 || yy >= h) continue;
-        for (int dx_ = -1; dx_ <= 1; ++dx_) {
-          const int xx = 2 * ox + dx_;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = 2 * ox + kx - 1;
           if (xx < 0 || xx >= w) continue;
           float f[8];
-          unpack8(x[((static_cast<long long>(b) * h + yy) * w + xx) * c8 + cc], act_fmt, f);
+          unpack8(__ldg(&x[((b * h + yy) * w + xx) * c8 + cc]), act_fmt, f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (f[i] > best[i]) { best[i] = f[i]; by[i] = yy; bx[i] = xx; }
+          for (int e = 0; e < 8; ++e)
+            if (f[e] > best[e]) { best[e] = f[e]; pos[e] = ky * 3 + kx; }
         }
       }
       float g[8];
-      unpack8(dy[((static_cast<long long>(b) * ho + oy) * wo + ox) * c8 + cc], grad_fmt, g);
+      unpack8(__ldg(&dy[((b * ho + oy) * wo + ox) * c8 + cc]), grad_fmt, g);
+      // window (j + wy, i + wx) sees block pixel (a, bb) at tap (ky, kx) = (a + 1 - 2 wy, bb + 1 - 2 wx)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (by[i] == iy && bx[i] == ix) acc[i] += g[i];
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+          const int ky = a + 1 - 2 * wy, kx = bb + 1 - 2 * wx;
+          if (ky < 0 || ky > 2 || kx < 0 || kx > 2) continue;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (pos[e] == ky * 3 + kx) acc[a * 2 + bb][e] += g[e];
+        }
     }
-  (void)xin;
-  if (accumulate) {
-    float f[8];
-    unpack8(dx[idx], grad_fmt, f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += f[i];
   }
-  dx[idx] = pack8(acc, grad_fmt);
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb) {
+      const long long o = ((b * h + 2 * j + a) * w + 2 * i + bb) * c8 + cc;
+      if (accumulate) {
+        float f[8];
+        unpack8(dx[o], grad_fmt, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[a * 2 + bb][e] += f[e];
+      }
+      dx[o] = pack8(acc[a * 2 + bb], grad_fmt);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -520,11 +568,12 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 static inline unsigned nblocks(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
-static inline int red_blocks(long long M, int C) {
+static inline int red_blocks(long long M, int C, int blocks_per_sm = 4) {
   const int rows_per_pass = RED_THREADS / (C / 8);
   long long want = (M + rows_per_pass * 8 - 1) / (rows_per_pass * 8);
   if (want < 1) want = 1;
-  return static_cast<int>(want < RED_MAX_BLOCKS ? want : RED_MAX_BLOCKS);
+  const int cap = blocks_per_sm * 148 < RED_MAX_BLOCKS ? blocks_per_sm * 148 : RED_MAX_BLOCKS;   // one resident wave
+  return static_cast<int>(want < cap ? want : cap);
 }
 
 }  // namespace fp
@@ -569,7 +618,7 @@ extern "C" int fp_bn_bwd(const void* dy, const void* y, const void* z, const flo
     return set_error(FP_ERR_ARG, "fp_bn_bwd: null argument");
   if ((C & 7) || RED_THREADS % (C / 8)) return set_error(FP_ERR_ARG, "fp_bn_bwd: unsupported C=%d", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nblk = red_blocks(M, C);
+  const int nblk = red_blocks(M, C, 3);
   const int rows_per_pass = RED_THREADS / (C / 8);
   col_reduce_kernel<1><<<nblk, RED_THREADS, rows_per_pass * 2 * C * sizeof(float), st>>>(
       static_cast<const uint4*>(dy), grad_dtype, relu ? static_cast<const uint4*>(y) : nullptr,
@@ -683,9 +732,10 @@ extern "C" int fp_grad_add(void* a, const void* b, long long n, int grad_dtype, 
 
 extern "C" int fp_maxpool3x3s2_bwd(const void* x, const void* dy, int batch, int h, int w, int c, int act_dtype,
                                    int grad_dtype, int accumulate, void* dx, void* stream) {
-  if (!x || !dy || !dx || (c & 7)) return set_error(FP_ERR_ARG, "fp_maxpool3x3s2_bwd: bad argument");
-  const long long n = static_cast<long long>(batch) * h * w * (c / 8);
-  maxpool_bwd_kernel<int><<<nblocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (!x || !dy || !dx || (c & 7) || (h & 1) || (w & 1))
+    return set_error(FP_ERR_ARG, "fp_maxpool3x3s2_bwd: bad argument (c %% 8, even h and w required)");
+  const long long n = static_cast<long long>(batch) * (h / 2) * (w / 2) * (c / 8);
+  maxpool_bwd_kernel<<<nblocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<const uint4*>(dy), batch, h, w, c / 8, act_dtype, grad_dtype, accumulate,
       static_cast<uint4*>(dx));
   FP_CHECK_LAUNCH("fp_maxpool3x3s2_bwd");

@@ -277,11 +277,12 @@ def test_bias_grad_and_adam(lib):
     assert (p - ref.detach()).abs().max() <= 1e-6
 
 
-@pytest.mark.parametrize('C,sigmoid', [(32, 1), (64, 0), (128, 1)])
-def test_head_kernels_match_autograd(lib, C, sigmoid):
+@pytest.mark.parametrize('shape', [(2, 9, 14), (2, 37, 70)])        # one ragged tile; several tiles, ragged edges
+@pytest.mark.parametrize('C,sigmoid', [(32, 1), (64, 0), (128, 1), (16, 0)])
+def test_head_kernels_match_autograd(lib, C, sigmoid, shape):
     """fp_head_conv_fwd / _dgrad / _wgrad (CUDA-core kernels of the 2-channel heads) against autograd."""
     g = torch.Generator().manual_seed(8)
-    b, h, w = 2, 9, 14
+    b, h, w = shape
     x = rnd(b, C, h, w, g=g).requires_grad_(True)
     wgt = rnd(2, C, 3, 3, g=g, scale=1.0 / (9 * C) ** 0.5).requires_grad_(True)
     bias = (torch.randn(2, generator=g).cuda() * 0.1).requires_grad_(True)
