@@ -56,6 +56,24 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t row
   return FP_OK;
 }
 
+// NHWC 16-bit activation tensor [n][h][w][c] -> box {box_c, box_w, 1, 1}; coordinates outside the tensor (negative or
+// past the end in w / h) are zero-filled, which is exactly a zero-padded convolution's halo
+int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t n, uint32_t box_c,
+                   uint32_t box_w, int swizzle_bytes) {
+  auto enc = get_encode();
+  if (enc == nullptr) return set_error(FP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {c, w, h, n};
+  cuuint64_t strides[3] = {c * 2, c * w * 2, c * w * h * 2};
+  cuuint32_t box[4] = {box_c, box_w, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(FP_ERR_CUDA, "cuTensorMapEncodeTiled(nhwc) failed: %d", static_cast<int>(r));
+  return FP_OK;
+}
+
 // [rows][width][cols] 16-bit tensor (cols contiguous) -> box {box_cols, box_width, 1}, SWIZZLE_128B; out-of-range
 // width positions are zero-filled, which masks the overhang of 128-pixel row segments
 int make_tmap_3d_sw128(CUtensorMap* out, const void* base, uint64_t cols, uint64_t width, uint64_t rows, uint32_t box_cols,

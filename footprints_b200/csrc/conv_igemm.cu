@@ -494,11 +494,13 @@ struct StripParams {
   IgemmParams b;             // geometry, epilogue, tile counts (m_tiles = batch*Ho*tiles_per_row)
   int tiles_per_row;         // ceil(Wo / 128)
   int cblocks;               // (C0 + C1) / CB
+  int x_via_tma;             // strips by one 4-D TMA box each (zero padding = out-of-bounds fill; single source, no upsample)
 };
 
 template <int BN, int CB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_constant__ CUtensorMap tmap_w) {
+conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_constant__ CUtensorMap tmap_w,
+                        const __grid_constant__ CUtensorMap tmap_x) {
   using Cfg = StripCfg<BN, CB>;
   constexpr int ROW_BYTES = Cfg::ROW_BYTES;
   constexpr int CPR = ROW_BYTES / 16;                    // 16-byte chunks per strip row
@@ -529,7 +531,7 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], NUM_PRODUCER_THREADS + 1);
+      mbar_init(&full_bar[s], sp.x_via_tma ? 1 : NUM_PRODUCER_THREADS + 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -538,6 +540,7 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmap_w);
+    if (sp.x_via_tma) tma_prefetch_desc(&tmap_x);
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
   tcgen05_fence_before();
@@ -546,7 +549,36 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int stages_per_tile = 3 * sp.cblocks;
 
-  if (warp < NUM_PRODUCER_WARPS) {
+  if (warp < NUM_PRODUCER_WARPS && sp.x_via_tma) {
+    // =============================== PRODUCER (TMA) ===============================
+    // one thread: per stage a {CB, 130, 1, 1} box of the NHWC input lands in the strip layout (the tensor map's swizzle
+    // is the strip's), rows / columns outside the image are zero-filled by the copy engine
+    if (tid == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const GatherGeom& g = p.g;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        const int xseg = m_tile % sp.tiles_per_row;
+        const int yrow = m_tile / sp.tiles_per_row;          // b * Ho + y
+        const int img = yrow / g.Ho;
+        const int y = yrow - img * g.Ho;
+        for (int dy = 0; dy < 3; ++dy)
+          for (int cb = 0; cb < sp.cblocks; ++cb) {
+            mbar_wait(&empty_bar[s], ph ^ 1, 21);
+            const uint32_t stage = smem_u32(stage0) + s * Cfg::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES + STRIP_PIX * ROW_BYTES);
+            tma_load_4d(stage, &tmap_x, &full_bar[s], cb * CB, xseg * BM - g.pad_l, y - g.pad_t + dy, img);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              tma_load_2d(stage + Cfg::A_BYTES + dx * Cfg::B_TILE, &tmap_w, &full_bar[s],
+                          ((dy * 3 + dx) * sp.cblocks + cb) * CB, n_tile * BN);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+      }
+    }
+  } else if (warp < NUM_PRODUCER_WARPS) {
     // =============================== PRODUCERS ===============================
     const int c = tid % CPR;   // 16-byte chunk of the strip row
     const int r0 = tid / CPR;  // strip rows r0 + ROWS_PER_PASS*i
@@ -717,7 +749,7 @@ static int strip_min_eff() {
 }
 
 template <int BN, int CB>
-static int launch_strip(const StripParams& sp, const CUtensorMap& tmap, cudaStream_t stream) {
+static int launch_strip(const StripParams& sp, const CUtensorMap& tmap, const CUtensorMap& tmap_x, cudaStream_t stream) {
   using Cfg = StripCfg<BN, CB>;
   static bool attr_set = false;
   auto kern = conv_igemm_strip_kernel<BN, CB>;
@@ -727,7 +759,7 @@ static int launch_strip(const StripParams& sp, const CUtensorMap& tmap, cudaStre
     attr_set = true;
   }
   const int grid = sp.b.total_tiles < num_sms() ? sp.b.total_tiles : num_sms();
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(sp, tmap);
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(sp, tmap, tmap_x);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "conv_igemm_strip launch (BN=%d): %s", BN, cudaGetErrorString(e));
   return FP_OK;
@@ -842,17 +874,28 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
                           static_cast<uint32_t>(d->bn), 64);
         if (rc != FP_OK) return rc;
       }
+      // zero-padded single-source inputs (every data-gradient full correlation): strips straight from the copy engine
+      CUtensorMap tmap_x;
+      memset(&tmap_x, 0, sizeof(tmap_x));
+      const char* xenv = getenv("FP_STRIP_TMA");
+      if (d->pad_mode == FP_PAD_ZERO && d->up0 == 0 && d->c1 == 0 && !(xenv && atoi(xenv) == 0)) {
+        rc = make_tmap_nhwc(&tmap_x, src0, static_cast<uint64_t>(d->c0), static_cast<uint64_t>(d->w0),
+                            static_cast<uint64_t>(d->h0), static_cast<uint64_t>(d->batch), static_cast<uint32_t>(cb),
+                            static_cast<uint32_t>(STRIP_PIX), cb * 2);
+        if (rc != FP_OK) return rc;
+        sp.x_via_tma = 1;
+      }
       if (cb == 64) {
         switch (d->bn) {
-          case 32: return launch_strip<32, 64>(sp, tmap_s, st);
-          case 64: return launch_strip<64, 64>(sp, tmap_s, st);
-          case 128: return launch_strip<128, 64>(sp, tmap_s, st);
+          case 32: return launch_strip<32, 64>(sp, tmap_s, tmap_x, st);
+          case 64: return launch_strip<64, 64>(sp, tmap_s, tmap_x, st);
+          case 128: return launch_strip<128, 64>(sp, tmap_s, tmap_x, st);
           default: break;
         }
       } else {
         switch (d->bn) {
-          case 32: return launch_strip<32, 32>(sp, tmap_s, st);
-          case 64: return launch_strip<64, 32>(sp, tmap_s, st);
+          case 32: return launch_strip<32, 32>(sp, tmap_s, tmap_x, st);
+          case 64: return launch_strip<64, 32>(sp, tmap_s, tmap_x, st);
           default: break;
         }
       }

@@ -19,6 +19,8 @@ int make_tmap_2d_sw128(CUtensorMap* out, const void* base, uint64_t cols, uint64
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows,
                  int swizzle_bytes);
 
+int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t n, uint32_t box_c,
+                   uint32_t box_w, int swizzle_bytes);
 int make_tmap_3d_sw128(CUtensorMap* out, const void* base, uint64_t cols, uint64_t width, uint64_t rows, uint32_t box_cols,
                        uint32_t box_width);
 

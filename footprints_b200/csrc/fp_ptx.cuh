@@ -126,6 +126,14 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // Blackwell tile::gather4: four arbitrary rows (r0..r3) x box-columns starting at column `col` of a 2-D tensor
 // land as four consecutive (swizzled) rows in shared memory; out-of-range rows are filled with zeros.
 __device__ __forceinline__ void tma_gather4_2d(uint32_t dst_smem, const CUtensorMap* m, uint64_t* bar, int col, int r0,

@@ -25,5 +25,6 @@ for kind, name, flops, a, b in prof:
     rows.append((ms, kind, name, flops / ms / 1e9))
     tot[kind] = tot.get(kind, 0) + ms
 print(tot)
-for ms, kind, name, tf in sorted(rows, reverse=True)[:45]:
+top = int(os.environ.get('TOP', '45'))
+for ms, kind, name, tf in sorted(rows, reverse=True)[:top]:
     print(f'{ms:8.3f} ms  {kind:6s} {name:28s} {tf:8.1f} TFLOP/s')
