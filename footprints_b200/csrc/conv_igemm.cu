@@ -115,71 +115,90 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
-// Drain `ncols_total` accumulator columns of this thread's row (TMEM lane) starting at column `col0`:
-// y = act(acc*scale + shift (+ residual)) -> 16-bit or fp32 NHWC row.  ACT and FMT are compile-time.
+// y = act(acc*scale + shift (+ residual)) -> 16-bit or fp32 NHWC row, for 16 accumulator columns held in registers.
 template <int ACT, int FMT>
-__device__ __forceinline__ void epilogue_cols(const IgemmParams& p, uint32_t tbase, int col0, int ncols_total, int n_base,
-                                              int m, bool row_ok, const float* s_scale, const float* s_shift) {
+__device__ __forceinline__ void epilogue_store16(const IgemmParams& p, const uint32_t* v, int j, int n_base, int m,
+                                                 const float* s_scale, const float* s_shift) {
   constexpr int CW = 16;
+  const int n0 = n_base + j;
+  if (n0 >= p.N) return;
+  float f[CW];
+#pragma unroll
+  for (int x = 0; x < CW; ++x) f[x] = __uint_as_float(v[x]) * s_scale[j + x] + s_shift[j + x];
+  const int ncols = min(CW, p.N - n0);
+  if (p.residual != nullptr) {
+    const uint8_t* rp = p.residual + (static_cast<size_t>(m) * p.res_ld + n0) * 2;
+    if (ncols == CW) {
+#pragma unroll
+      for (int x = 0; x < CW / 8; ++x) {
+        const uint4 r = *reinterpret_cast<const uint4*>(rp + x * 16);
+        float2 t;
+        t = unpack2t<FMT>(r.x); f[x * 8 + 0] += t.x; f[x * 8 + 1] += t.y;
+        t = unpack2t<FMT>(r.y); f[x * 8 + 2] += t.x; f[x * 8 + 3] += t.y;
+        t = unpack2t<FMT>(r.z); f[x * 8 + 4] += t.x; f[x * 8 + 5] += t.y;
+        t = unpack2t<FMT>(r.w); f[x * 8 + 6] += t.x; f[x * 8 + 7] += t.y;
+      }
+    } else {
+#pragma unroll
+      for (int x = 0; x < CW; ++x)
+        if (x < ncols) f[x] += unpack2t<FMT>(*reinterpret_cast<const uint16_t*>(rp + x * 2)).x;
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < CW; ++x) f[x] = apply_act<ACT>(f[x]);
+  if (p.out_f32) {
+    float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + n0;
+    if (ncols == CW && (p.out_ld & 3) == 0) {
+#pragma unroll
+      for (int x = 0; x < CW / 4; ++x)
+        *reinterpret_cast<float4*>(op + 4 * x) = make_float4(f[4 * x], f[4 * x + 1], f[4 * x + 2], f[4 * x + 3]);
+    } else {
+#pragma unroll
+      for (int x = 0; x < CW; ++x) if (x < ncols) op[x] = f[x];
+    }
+  } else {
+    uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (static_cast<size_t>(m) * p.out_ld + n0) * 2;
+    if (ncols == CW && (p.out_ld & 7) == 0) {
+#pragma unroll
+      for (int x = 0; x < CW / 8; ++x) {
+        uint4 o;
+        o.x = pack2t<FMT>(f[8 * x], f[8 * x + 1]);
+        o.y = pack2t<FMT>(f[8 * x + 2], f[8 * x + 3]);
+        o.z = pack2t<FMT>(f[8 * x + 4], f[8 * x + 5]);
+        o.w = pack2t<FMT>(f[8 * x + 6], f[8 * x + 7]);
+        *reinterpret_cast<uint4*>(op + 16 * x) = o;
+      }
+    } else {
+#pragma unroll
+      for (int x = 0; x < CW; ++x)
+        if (x < ncols) *reinterpret_cast<uint16_t*>(op + 2 * x) = static_cast<uint16_t>(pack2t<FMT>(f[x], 0.f) & 0xFFFF);
+    }
+  }
+}
+
+// Drain NC accumulator columns of this thread's row (TMEM lane) starting at column `col0`.  The columns are pulled into
+// registers in passes of <= 32; as soon as the LAST pass's TMEM reads have completed the accumulator buffer is handed
+// back to the MMA warp (arrive on `release_bar`), so scale/shift, residual, activation, packing and the global stores
+// run off the tensor pipe's critical path (they used to delay the next-but-one tile's first MMA).
+template <int ACT, int FMT, int NC>
+__device__ __forceinline__ void epilogue_cols(const IgemmParams& p, uint32_t tbase, int col0, int n_base, int m, bool row_ok,
+                                              const float* s_scale, const float* s_shift, uint64_t* release_bar,
+                                              int lane) {
+  constexpr int PASS = NC > 32 ? 32 : NC;
 #pragma unroll 1
-  for (int j = col0; j < col0 + ncols_total; j += CW) {
-    uint32_t v[CW];
-    tmem_ld_32x32b_x16(tbase + j, v);
+  for (int c0 = 0; c0 < NC; c0 += PASS) {
+    uint32_t v[PASS];
+#pragma unroll
+    for (int j = 0; j < PASS; j += 16) tmem_ld_32x32b_x16(tbase + col0 + c0 + j, *reinterpret_cast<uint32_t(*)[16]>(&v[j]));
     tmem_ld_wait();
-    const int n0 = n_base + j;
-    if (row_ok && n0 < p.N) {
-      float f[CW];
+    if (c0 + PASS >= NC) {
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(release_bar);
+    }
+    if (row_ok) {
 #pragma unroll
-      for (int x = 0; x < CW; ++x) f[x] = __uint_as_float(v[x]) * s_scale[j + x] + s_shift[j + x];
-      const int ncols = min(CW, p.N - n0);
-      if (p.residual != nullptr) {
-        const uint8_t* rp = p.residual + (static_cast<size_t>(m) * p.res_ld + n0) * 2;
-        if (ncols == CW) {
-#pragma unroll
-          for (int x = 0; x < CW / 8; ++x) {
-            const uint4 r = *reinterpret_cast<const uint4*>(rp + x * 16);
-            float2 t;
-            t = unpack2t<FMT>(r.x); f[x * 8 + 0] += t.x; f[x * 8 + 1] += t.y;
-            t = unpack2t<FMT>(r.y); f[x * 8 + 2] += t.x; f[x * 8 + 3] += t.y;
-            t = unpack2t<FMT>(r.z); f[x * 8 + 4] += t.x; f[x * 8 + 5] += t.y;
-            t = unpack2t<FMT>(r.w); f[x * 8 + 6] += t.x; f[x * 8 + 7] += t.y;
-          }
-        } else {
-#pragma unroll
-          for (int x = 0; x < CW; ++x)
-            if (x < ncols) f[x] += unpack2t<FMT>(*reinterpret_cast<const uint16_t*>(rp + x * 2)).x;
-        }
-      }
-#pragma unroll
-      for (int x = 0; x < CW; ++x) f[x] = apply_act<ACT>(f[x]);
-      if (p.out_f32) {
-        float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_ld + n0;
-        if (ncols == CW && (p.out_ld & 3) == 0) {
-#pragma unroll
-          for (int x = 0; x < CW / 4; ++x)
-            *reinterpret_cast<float4*>(op + 4 * x) = make_float4(f[4 * x], f[4 * x + 1], f[4 * x + 2], f[4 * x + 3]);
-        } else {
-#pragma unroll
-          for (int x = 0; x < CW; ++x) if (x < ncols) op[x] = f[x];
-        }
-      } else {
-        uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (static_cast<size_t>(m) * p.out_ld + n0) * 2;
-        if (ncols == CW && (p.out_ld & 7) == 0) {
-#pragma unroll
-          for (int x = 0; x < CW / 8; ++x) {
-            uint4 o;
-            o.x = pack2t<FMT>(f[8 * x], f[8 * x + 1]);
-            o.y = pack2t<FMT>(f[8 * x + 2], f[8 * x + 3]);
-            o.z = pack2t<FMT>(f[8 * x + 4], f[8 * x + 5]);
-            o.w = pack2t<FMT>(f[8 * x + 6], f[8 * x + 7]);
-            *reinterpret_cast<uint4*>(op + 16 * x) = o;
-          }
-        } else {
-#pragma unroll
-          for (int x = 0; x < CW; ++x)
-            if (x < ncols) *reinterpret_cast<uint16_t*>(op + 2 * x) = static_cast<uint16_t>(pack2t<FMT>(f[x], 0.f) & 0xFFFF);
-        }
-      }
+      for (int j = 0; j < PASS; j += 16) epilogue_store16<ACT, FMT>(p, &v[j], col0 + c0 + j, n_base, m, s_scale, s_shift);
     }
   }
 }
@@ -389,18 +408,22 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
     const int col_begin = (BN >= 32) ? half * COLS_PER_HALF : 0;
     const bool active = (BN >= 32) || (half == 0);
     uint32_t ti = 0;
+    int cur_n = -1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
       const uint32_t acc = ti & 1;
-      named_bar_sync(1, NUM_EPI_THREADS);          // everyone finished reading the previous tile's scale/shift
-      for (int j = e; j < BN; j += NUM_EPI_THREADS) {
-        const int n = n_tile * BN + j;
-        s_scale[j] = (p.scale != nullptr && n < p.N) ? p.scale[n] : 1.f;
-        s_shift[j] = (p.shift != nullptr && n < p.N) ? p.shift[n] : 0.f;
+      if (n_tile != cur_n) {     // (re)load the per-channel scale / shift only when the channel tile changes: the two
+        cur_n = n_tile;          // barriers and the global-load latency sat on every tile's epilogue critical path
+        named_bar_sync(1, NUM_EPI_THREADS);        // everyone finished reading the previous tile's scale/shift
+        for (int j = e; j < BN; j += NUM_EPI_THREADS) {
+          const int n = n_tile * BN + j;
+          s_scale[j] = (p.scale != nullptr && n < p.N) ? p.scale[n] : 1.f;
+          s_shift[j] = (p.shift != nullptr && n < p.N) ? p.shift[n] : 0.f;
+        }
+        named_bar_sync(1, NUM_EPI_THREADS);
       }
-      named_bar_sync(1, NUM_EPI_THREADS);
-      mbar_wait<128>(&tmem_full_bar[acc], (ti >> 1) & 1, 4);
+      mbar_wait<32>(&tmem_full_bar[acc], (ti >> 1) & 1, 4);
       if ((kTriage && p.debug & 16) && blockIdx.x == 0 && e == 0 && ti < 1024) g_trace[2][2 * ti] = clock64();
       tcgen05_fence_after();
       const int m = m_tile * BM + row;
@@ -408,7 +431,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
       if (active) {
         const uint32_t tbase = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
         const bool skip = (kTriage && p.debug & 4) != 0;
-#define FP_EPI(A, F) epilogue_cols<A, F>(p, tbase, col_begin, COLS_PER_HALF, n_tile * BN, m, m_ok && !skip, s_scale, s_shift)
+#define FP_EPI(A, F) epilogue_cols<A, F, COLS_PER_HALF>(p, tbase, col_begin, n_tile * BN, m, m_ok && !skip, s_scale, s_shift, &tmem_empty_bar[acc], lane)
         if (p.fmt == FP_BF16) {
           switch (p.act) {
             case FP_ACT_RELU: FP_EPI(FP_ACT_RELU, FP_BF16); break;
@@ -426,10 +449,12 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
         }
 #undef FP_EPI
       }
-      tcgen05_fence_before();
-      __syncwarp();
+      if (!active) {          // BN < 32: the second column half has nothing to read, it only releases the buffer
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if ((kTriage && p.debug & 16) && blockIdx.x == 0 && e == 0 && ti < 1024) g_trace[2][2 * ti + 1] = clock64();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
 
@@ -689,6 +714,7 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
     const int col_begin = (BN >= 32) ? half * COLS_PER_HALF : 0;
     const bool active = (BN >= 32) || (half == 0);
     uint32_t ti = 0;
+    int cur_n = -1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const int m_tile = tile / p.n_tiles;
       const int n_tile = tile - m_tile * p.n_tiles;
@@ -696,20 +722,23 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
       const int yrow = m_tile / sp.tiles_per_row;
       const int x0 = xseg * BM;
       const uint32_t acc = ti & 1;
-      named_bar_sync(1, NUM_EPI_THREADS);
-      for (int j = e; j < BN; j += NUM_EPI_THREADS) {
-        const int n = n_tile * BN + j;
-        s_scale[j] = (p.scale != nullptr && n < p.N) ? p.scale[n] : 1.f;
-        s_shift[j] = (p.shift != nullptr && n < p.N) ? p.shift[n] : 0.f;
+      if (n_tile != cur_n) {
+        cur_n = n_tile;
+        named_bar_sync(1, NUM_EPI_THREADS);
+        for (int j = e; j < BN; j += NUM_EPI_THREADS) {
+          const int n = n_tile * BN + j;
+          s_scale[j] = (p.scale != nullptr && n < p.N) ? p.scale[n] : 1.f;
+          s_shift[j] = (p.shift != nullptr && n < p.N) ? p.shift[n] : 0.f;
+        }
+        named_bar_sync(1, NUM_EPI_THREADS);
       }
-      named_bar_sync(1, NUM_EPI_THREADS);
-      mbar_wait<128>(&tmem_full_bar[acc], (ti >> 1) & 1, 24);
+      mbar_wait<32>(&tmem_full_bar[acc], (ti >> 1) & 1, 24);
       tcgen05_fence_after();
       const int m = yrow * p.g.Wo + x0 + row;
       const bool m_ok = (x0 + row) < p.g.Wo;
       if (active) {
         const uint32_t tbase = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-#define FP_EPI(A, F) epilogue_cols<A, F>(p, tbase, col_begin, COLS_PER_HALF, n_tile * BN, m, m_ok, s_scale, s_shift)
+#define FP_EPI(A, F) epilogue_cols<A, F, COLS_PER_HALF>(p, tbase, col_begin, n_tile * BN, m, m_ok, s_scale, s_shift, &tmem_empty_bar[acc], lane)
         if (p.fmt == FP_BF16) {
           switch (p.act) {
             case FP_ACT_RELU: FP_EPI(FP_ACT_RELU, FP_BF16); break;
@@ -727,9 +756,11 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
         }
 #undef FP_EPI
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (!active) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      }
     }
   }
 
