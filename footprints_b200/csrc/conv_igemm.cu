@@ -511,8 +511,10 @@ struct StripCfg {
   static constexpr int STAGE_BYTES = A_BYTES + (B_BYTES + 1023) / 1024 * 1024;
   static constexpr int STAGES = (CB == 32) ? 8 : ((BN <= 32) ? 6 : (BN <= 64 ? 5 : 3));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 2 * BN * 4 +
-                                    2 * (2 * STRIP_ROWS + 8) * 4;
+  static constexpr int MAX_STAGES = 8;
+  // everything but the stage ring and the resident filter: alignment slack, mbarriers, TMEM pointer, scale/shift, maps
+  static constexpr int FIXED_BYTES = 1024 + (2 * MAX_STAGES + 5) * 8 + 16 + 2 * BN * 4 + 2 * (2 * STRIP_ROWS + 8) * 4;
+  static constexpr int SMEM_MAX = 232448;      // 227 KB opt-in limit per CTA
 };
 
 struct StripParams {
@@ -520,6 +522,14 @@ struct StripParams {
   int tiles_per_row;         // ceil(Wo / 128)
   int cblocks;               // (C0 + C1) / CB
   int x_via_tma;             // strips by one 4-D TMA box each (zero padding = out-of-bounds fill; single source, no upsample)
+  // weight residency: when the layer's whole packed filter (9 * cblocks tiles of [BN][CB]) fits next to the strip
+  // ring it is loaded ONCE per CTA instead of once per output tile.  The thin 192x640 / 96x320 layers are bound by
+  // L2->SM bandwidth (~20 B/clk/SM with all SMs streaming), and re-fetching 18-147 KB of weights for every 128-pixel
+  // tile was 40-60 % of that traffic.
+  int w_resident;
+  int stages;                // pipeline depth actually used (<= StripCfg::MAX_STAGES)
+  int stage_bytes;           // A_BYTES when resident (no per-stage weight area), else STAGE_BYTES
+  int w_bytes;               // resident filter bytes (0 when streaming)
 };
 
 template <int BN, int CB>
@@ -532,18 +542,22 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
   constexpr int ROWS_PER_PASS = NUM_PRODUCER_THREADS / CPR;
   constexpr uint64_t LAYOUT = (CB == 64) ? 2ull : 4ull;  // UMMA layout type: SWIZZLE_128B / SWIZZLE_64B
   constexpr uint32_t SBO = 8 * ROW_BYTES;                // 8-row swizzle group
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int MAX_STAGES = Cfg::MAX_STAGES;
+  const int STAGES = sp.stages;
+  const int STAGE_BYTES = sp.stage_bytes;
   const IgemmParams& p = sp.b;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* stage0 = smem;                                               // [STAGES][strip | B0 | B1 | B2]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint8_t* stage0 = smem;                                               // [STAGES][strip (| B0 | B1 | B2 when streaming)]
+  uint8_t* w_res = smem + STAGES * STAGE_BYTES;                         // resident filter: [9 * cblocks][BN][CB]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(w_res + sp.w_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* w_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
   float* s_scale = reinterpret_cast<float*>(tmem_ptr_smem + 4);
   float* s_shift = s_scale + BN;
   // per tile: element offset of every strip pixel inside its source row (0xFFFFFFFF = padding zero), for both
@@ -563,9 +577,15 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
     }
+    mbar_init(w_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap_w);
     if (sp.x_via_tma) tma_prefetch_desc(&tmap_x);
+    if (sp.w_resident) {
+      mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(sp.w_bytes));
+      for (int t = 0; t < 9 * sp.cblocks; ++t)
+        tma_load_2d(smem_u32(w_res) + t * Cfg::B_TILE, &tmap_w, w_bar, t * CB, 0);
+    }
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
   tcgen05_fence_before();
@@ -592,13 +612,15 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
         for (int dy = 0; dy < 3; ++dy)
           for (int cb = 0; cb < sp.cblocks; ++cb) {
             mbar_wait(&empty_bar[s], ph ^ 1, 21);
-            const uint32_t stage = smem_u32(stage0) + s * Cfg::STAGE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES + STRIP_PIX * ROW_BYTES);
+            const uint32_t stage = smem_u32(stage0) + s * STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[s], (sp.w_resident ? 0 : Cfg::B_BYTES) + STRIP_PIX * ROW_BYTES);
             tma_load_4d(stage, &tmap_x, &full_bar[s], cb * CB, xseg * BM - g.pad_l, y - g.pad_t + dy, img);
+            if (!sp.w_resident) {
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx)
-              tma_load_2d(stage + Cfg::A_BYTES + dx * Cfg::B_TILE, &tmap_w, &full_bar[s],
-                          ((dy * 3 + dx) * sp.cblocks + cb) * CB, n_tile * BN);
+              for (int dx = 0; dx < 3; ++dx)
+                tma_load_2d(stage + Cfg::A_BYTES + dx * Cfg::B_TILE, &tmap_w, &full_bar[s],
+                            ((dy * 3 + dx) * sp.cblocks + cb) * CB, n_tile * BN);
+            }
             if (++s == STAGES) { s = 0; ph ^= 1; }
           }
       }
@@ -641,13 +663,17 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
       for (int dy = 0; dy < 3; ++dy) {
         for (int cb = 0; cb < sp.cblocks; ++cb) {
           mbar_wait(&empty_bar[s], ph ^ 1, 21);
-          const uint32_t stage = smem_u32(stage0) + s * Cfg::STAGE_BYTES;
+          const uint32_t stage = smem_u32(stage0) + s * STAGE_BYTES;
           if (tid == 0) {
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES);
+            if (sp.w_resident) {
+              mbar_arrive(&full_bar[s]);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[s], Cfg::B_BYTES);
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx)
-              tma_load_2d(stage + Cfg::A_BYTES + dx * Cfg::B_TILE, &tmap_w, &full_bar[s],
-                          ((dy * 3 + dx) * sp.cblocks + cb) * CB, n_tile * BN);
+              for (int dx = 0; dx < 3; ++dx)
+                tma_load_2d(stage + Cfg::A_BYTES + dx * Cfg::B_TILE, &tmap_w, &full_bar[s],
+                            ((dy * 3 + dx) * sp.cblocks + cb) * CB, n_tile * BN);
+            }
           }
           const int ch = cb * CB;
           const bool second = ch >= g.C0;
@@ -679,26 +705,41 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
       uint32_t ti = 0;
       int s = 0;
       uint32_t ph = 0;
+      if (sp.w_resident) mbar_wait(w_bar, 0, 25);
+      constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (static_cast<uint32_t>(LAYOUT) << 29);   // SBO, version 1, layout
+      auto mk_desc = [](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(DESC_HI) << 32) | lo; };
+      const uint32_t stage0_lo = ((smem_u32(stage0) >> 4) & 0x3FFF) | (1u << 16);                 // LBO = 16 bytes
+      const uint32_t wres_lo = ((smem_u32(w_res) >> 4) & 0x3FFF) | (1u << 16);
+      const uint32_t stage_step = static_cast<uint32_t>(STAGE_BYTES) >> 4;
+      const uint32_t b_step = sp.w_resident ? sp.cblocks * (Cfg::B_TILE >> 4) : (Cfg::B_TILE >> 4);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
         const uint32_t acc = ti & 1;
         mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1, 22);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t b_tile = 0;                       // resident filter tile (dy*3*cblocks + cb) in units of B_TILE/16
+        int cbi = 0;
         for (int st = 0; st < stages_per_tile; ++st) {
           mbar_wait(&full_bar[s], ph, 23);
           tcgen05_fence_after();
-          const uint32_t stage = smem_u32(stage0) + s * Cfg::STAGE_BYTES;
+          // descriptor low words: (address >> 4) | LBO field; all strip / filter addresses are < 256 KB, so the tap,
+          // K-step and stage offsets are plain additions (no re-masking) -- the single issuing thread is the critical
+          // resource on the thin layers, every instruction between two UTCHMMAs counts
+          const uint32_t a_lo = stage0_lo + static_cast<uint32_t>(s) * stage_step;
+          const uint32_t b_lo = sp.w_resident ? wres_lo + b_tile : a_lo + (Cfg::A_BYTES >> 4);
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
             // the tap's A operand = the strip advanced by dx pixels (whole rows)
-            const uint64_t a_desc = umma_smem_desc(stage + dx * ROW_BYTES, 16, SBO, LAYOUT);
-            const uint64_t b_desc = umma_smem_desc(stage + Cfg::A_BYTES + dx * Cfg::B_TILE, 16, SBO, LAYOUT);
 #pragma unroll
             for (int k = 0; k < CB / 16; ++k)
-              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (st | dx | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, mk_desc(a_lo + dx * (ROW_BYTES >> 4) + 2 * k), mk_desc(b_lo + dx * b_step + 2 * k), idesc,
+                       (dx | k) != 0 ? 1u : (st != 0 ? 1u : 0u));
           }
           umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
+          // next stage = next channel block, then next filter row (tile index (dy*3 + dx)*cblocks + cb)
+          if (++cbi == sp.cblocks) { cbi = 0; b_tile += (2 * sp.cblocks + 1) * (Cfg::B_TILE >> 4); }
+          else b_tile += Cfg::B_TILE >> 4;
         }
         umma_commit(&tmem_full_bar[acc]);
       }
@@ -780,17 +821,34 @@ static int strip_min_eff() {
 }
 
 template <int BN, int CB>
-static int launch_strip(const StripParams& sp, const CUtensorMap& tmap, const CUtensorMap& tmap_x, cudaStream_t stream) {
+static int launch_strip(const StripParams& sp_in, const CUtensorMap& tmap, const CUtensorMap& tmap_x, cudaStream_t stream) {
   using Cfg = StripCfg<BN, CB>;
   static bool attr_set = false;
   auto kern = conv_igemm_strip_kernel<BN, CB>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(strip smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_MAX);
+    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(strip smem=%d): %s", Cfg::SMEM_MAX, cudaGetErrorString(e));
     attr_set = true;
   }
+  StripParams sp = sp_in;
+  // resident filter if it fits beside >= 3 strip stages (single channel tile only), else stream it per stage
+  const char* wenv = getenv("FP_STRIP_WRES");
+  const int w_bytes = 9 * sp.cblocks * Cfg::B_TILE;
+  const int room = Cfg::SMEM_MAX - Cfg::FIXED_BYTES - w_bytes;
+  if (sp.b.n_tiles == 1 && room >= 3 * Cfg::A_BYTES && !(wenv && atoi(wenv) == 0)) {
+    sp.w_resident = 1;
+    sp.w_bytes = w_bytes;
+    sp.stage_bytes = Cfg::A_BYTES;
+    sp.stages = room / Cfg::A_BYTES < Cfg::MAX_STAGES ? room / Cfg::A_BYTES : Cfg::MAX_STAGES;
+  } else {
+    sp.w_resident = 0;
+    sp.w_bytes = 0;
+    sp.stage_bytes = Cfg::STAGE_BYTES;
+    sp.stages = Cfg::STAGES;
+  }
+  const int smem_bytes = Cfg::FIXED_BYTES + sp.stages * sp.stage_bytes + sp.w_bytes;
   const int grid = sp.b.total_tiles < num_sms() ? sp.b.total_tiles : num_sms();
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(sp, tmap, tmap_x);
+  kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(sp, tmap, tmap_x);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "conv_igemm_strip launch (BN=%d): %s", BN, cudaGetErrorString(e));
   return FP_OK;
