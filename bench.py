@@ -282,10 +282,25 @@ def main():
         f_igemm = sum(agg[k][1] for k in ('fwd', 'dgrad') if k in agg)
         n_igemm = sum(agg[k][2] for k in ('fwd', 'dgrad') if k in agg)
         ach = f_igemm / (t_igemm * 1e-3) / 1e12 if t_igemm > 0 else 0.0
-        roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel (fwd + dgrad launches)', 'achieved': ach, 'peak': peak,
+        # longest single launch of that class, timed live; its DRAM traffic comes from the committed `ncu --set full`
+        # capture of the same launch (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum)
+        top = max((x for x in prof if x[0] in ('fwd', 'dgrad')), key=lambda x: x[3].elapsed_time(x[4]), default=None)
+        traffic, top_launch = None, None
+        if top is not None:
+            t_top = top[3].elapsed_time(top[4])
+            top_launch = {'layer': top[1], 'kind': top[0], 'ms': t_top, 'tflops': top[2] / (t_top * 1e-3) / 1e12}
+            try:
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+                key = top[1].split('.', 1)[-1] + '/' + top[0]          # 'mask.o4.c1' -> 'o4.c1/fwd'
+                if B == 64 and (H, W) == (192, 640) and key in tj['bytes_per_launch']:
+                    traffic = tj['bytes_per_launch'][key]
+            except (OSError, KeyError, ValueError):
+                pass
+        roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel + conv_igemm_strip_kernel (tcgen05 implicit GEMM; all fwd + dgrad launches of a step)',
+                    'achieved': ach, 'peak': peak,
                     'unit': 'TFLOP/s', 'frac': ach / peak,
                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback (B200_PROFILING.md, sustained)',
-                    'traffic': None, 'launches': n_igemm, 'ms_per_step_in_kernel': t_igemm,
+                    'traffic': traffic, 'traffic_of': top_launch, 'launches': n_igemm, 'ms_per_step_in_kernel': t_igemm,
                     'algorithmic_gflop_per_step': f_igemm / 1e9,
                     'by_kind': {k: {'ms': v[0], 'tflops': (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0), 'launches': v[2]}
                                 for k, v in agg.items()}}

@@ -546,7 +546,9 @@ static WgradPlan wgrad_plan(const FpConvDesc* d) {
   w.k_groups = (w.k_chunks + w.chunks_per_group - 1) / w.chunks_per_group;
   w.co_tiles = (d->cout + 127) / 128;
   const int base = w.k_groups * w.co_tiles;
-  int want = (2 * num_sms() + base - 1) / base;
+  // one CTA is resident per SM: never exceed two full waves (rounding UP used to leave a third wave of 1-4 CTAs,
+  // i.e. +50 % on the 68 general weight-gradient launches of a step)
+  int want = 2 * num_sms() / base;
   if (want < 1) want = 1;
   if (want > w.num_pix_blocks) want = w.num_pix_blocks;
   w.blocks_per_split = (w.num_pix_blocks + want - 1) / want;

@@ -367,6 +367,7 @@ head_dgrad_kernel(const uint4* __restrict__ dz8 /*[B][H][W][8] 16-bit, ch 0..1 v
 // with every thread producing 4 pixels x 16 channels per pass (weight pairs broadcast from shared memory are used for 4
 // pixels, G values for 16 channels) and writing whole 32-byte sectors.
 constexpr int HD_SMEM_G = 9 * HT_ROWS * HT_COLS * static_cast<int>(sizeof(float2));     // 36 KB
+constexpr int HD_SMEM_DZ = (HT_ROWS + 2) * (HT_COLS + 2) * static_cast<int>(sizeof(float2));
 
 __global__ void __launch_bounds__(HT_THREADS)
 head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ w, int H, int W, int C, int tiles_x,
@@ -374,7 +375,8 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
                        uint4* __restrict__ dst) {
   extern __shared__ __align__(16) uint8_t hd_smem[];
   float2* G = reinterpret_cast<float2*>(hd_smem);                       // [9][16*32]
-  float2* sw = reinterpret_cast<float2*>(hd_smem + HD_SMEM_G);          // [9][C]
+  float2* dzs = reinterpret_cast<float2*>(hd_smem + HD_SMEM_G);         // [18][34] dZ halo tile
+  float2* sw = dzs + (HT_ROWS + 2) * (HT_COLS + 2);                     // [9][C]
   const int tid = threadIdx.x;
   int bid = blockIdx.x;
   const int tx0 = (bid % tiles_x) * HT_COLS; bid /= tiles_x;
@@ -385,9 +387,24 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
     const int t = i / C, c = i - t * C;
     sw[i] = make_float2(w[(0 * C + c) * 9 + t], w[(1 * C + c) * 9 + t]);
   }
-  for (int i = tid; i < 9 * HT_ROWS * HT_COLS; i += HT_THREADS) {
+  // dZ halo tile (1 pixel each side, zero outside the image) staged once; every G term lies inside it
+  for (int i = tid; i < (HT_ROWS + 2) * (HT_COLS + 2); i += HT_THREADS) {
+    const int hy = i / (HT_COLS + 2), hx = i - hy * (HT_COLS + 2);
+    const int qy = ty0 + hy - 1, qx = tx0 + hx - 1;
+    float2 d = make_float2(0.f, 0.f);
+    if (qy >= 0 && qy < H && qx >= 0 && qx < W)
+      d = h_up2(__ldg(reinterpret_cast<const uint32_t*>(dz8 + (img * H + qy) * W + qx)), grad_fmt);
+    dzs[i] = d;
+  }
+  __syncthreads();
+  // tiles that hold none of the rows 1, H-2 / columns 1, W-2 have no reflected terms: G[t][p] is just dZ shifted by the
+  // tap, read straight from the halo tile (3/4 of the tiles at 192x640) -- the G table is only built for border tiles
+  const bool interior = !(ty0 <= 1) && !(ty0 <= H - 2 && H - 2 < ty0 + HT_ROWS) &&
+                        !(tx0 <= 1) && !(tx0 <= W - 2 && W - 2 < tx0 + HT_COLS);
+  for (int i = interior ? 9 * HT_ROWS * HT_COLS : tid; i < 9 * HT_ROWS * HT_COLS; i += HT_THREADS) {
     const int t = i / (HT_ROWS * HT_COLS), pix = i - t * (HT_ROWS * HT_COLS);
-    const int py = ty0 + pix / HT_COLS, px = tx0 + (pix % HT_COLS);
+    const int ry = pix / HT_COLS, rx = pix - ry * HT_COLS;
+    const int py = ty0 + ry, px = tx0 + rx;
     const int tyy = t / 3, txx = t - tyy * 3;
     float2 g = make_float2(0.f, 0.f);
     if (py < H && px < W) {
@@ -404,7 +421,7 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
         for (int ix = 0; ix < nx; ++ix) {
           const int qx = vx[ix] - txx + 1;
           if (qx < 0 || qx >= W) continue;
-          const float2 d = h_up2(__ldg(reinterpret_cast<const uint32_t*>(dz8 + (img * H + qy) * W + qx)), grad_fmt);
+          const float2 d = dzs[(qy - ty0 + 1) * (HT_COLS + 2) + (qx - tx0 + 1)];
           g.x += d.x; g.y += d.y;
         }
       }
@@ -423,8 +440,13 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       float2 g[4];
+      if (interior) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) g[r] = G[t * (HT_ROWS * HT_COLS) + (ly + r) * HT_COLS + lx];
+        for (int r = 0; r < 4; ++r) g[r] = dzs[(ly + r + 2 - t / 3) * (HT_COLS + 2) + lx + 2 - t % 3];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g[r] = G[t * (HT_ROWS * HT_COLS) + (ly + r) * HT_COLS + lx];
+      }
       const float2* wt = sw + t * C + cb;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -600,11 +622,11 @@ extern "C" int fp_head_conv_dgrad(const void* dz8, const float* w_oihw, int batc
   const char* tenv = getenv("FP_HEAD_TILE");
   if (c % 16 == 0 && !(tenv && atoi(tenv) == 0)) {
     const int tiles_x = (w + HT_COLS - 1) / HT_COLS, tiles_y = (h + HT_ROWS - 1) / HT_ROWS;
-    const int smem = HD_SMEM_G + 9 * c * static_cast<int>(sizeof(float2));
+    const int smem = HD_SMEM_G + HD_SMEM_DZ + 9 * c * static_cast<int>(sizeof(float2));
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(head_dgrad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           HD_SMEM_G + 9 * HEAD_MAX_C * static_cast<int>(sizeof(float2)));
+                                           HD_SMEM_G + HD_SMEM_DZ + 9 * HEAD_MAX_C * static_cast<int>(sizeof(float2)));
       if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(head dgrad): %s", cudaGetErrorString(e));
       attr_set = true;
     }

@@ -175,7 +175,7 @@ int fp_act_bwd(const void* dy, const void* y, int act, long long n, int act_dtyp
                void* stream);
 /* a += b on 16-bit gradient buffers, n elements (multiple of 8). */
 int fp_grad_add(void* a, const void* b, long long n, int grad_dtype, void* stream);
-/* MaxPool2d(3,2,1) backward (first maximum wins ties). */
+/* MaxPool2d(3,2,1) backward (first maximum wins ties); h and w must be even (one thread per 2x2 input block). */
 int fp_maxpool3x3s2_bwd(const void* x, const void* dy, int batch, int h, int w, int c, int act_dtype, int grad_dtype,
                         int accumulate, void* dx, void* stream);
 
