@@ -212,8 +212,12 @@ conv_wgrad_kernel(const __grid_constant__ WgradParams p, const __grid_constant__
 // (SWIZZLE_128B / 64B / 32B).  A CTA owns (128 output channels) x (ndy filter rows) x (ncb channel blocks) x 3 taps x CB
 // TMEM columns for a range of row segments; dZ arrives by a 3-D TMA box whose out-of-row pixels are zero-filled.
 // ==================================================================================================
-constexpr int WS_STRIP_PIX = 130;
-constexpr int WS_STRIP_ROWS = 136;
+// A row segment is `seg` output pixels (any multiple of 16 up to 160: K of the MMA is the pixel axis, so unlike the
+// forward strips the segment need not be 128): Wo = 160 / 320 / 640 -> 160, Wo = 80 -> 80, Wo = 40 -> 48.
+constexpr int WS_MAX_SEG = 160;
+constexpr int WS_STRIP_ROWS = 168;                             // >= WS_MAX_SEG + 2, whole 8-row swizzle groups
+constexpr int WS_DZ_SUB_MAX = WS_MAX_SEG * 128;                // one 64-channel dZ block of a segment
+constexpr int WS_DZ_STAGE_MAX = 2 * WS_DZ_SUB_MAX;
 constexpr int WS_X_STAGES = 6;
 constexpr int WS_DZ_STAGES = 2;
 constexpr int WS_MAX_COLS = 384;                               // accumulator columns per CTA
@@ -221,14 +225,15 @@ constexpr int WS_BAR_BYTES = 192;
 constexpr int WS_XOFF_WORDS = 2 * WS_STRIP_ROWS + 8;
 
 template <int CB> constexpr int ws_smem_bytes() {
-  return 1024 + WS_X_STAGES * WS_STRIP_ROWS * CB * 2 + WS_DZ_STAGES * WG_DZ_STAGE_BYTES + WS_BAR_BYTES + 16 +
+  return 1024 + WS_X_STAGES * WS_STRIP_ROWS * CB * 2 + WS_DZ_STAGES * WS_DZ_STAGE_MAX + WS_BAR_BYTES + 16 +
          2 * WS_XOFF_WORDS * 4;
 }
 
 struct WgradStripParams {
   GatherGeom g;
   int Cout, kpad, cin;
-  int tiles_per_row;          // ceil(Wo / 128)
+  int seg;                    // pixels per row segment (multiple of 16, <= WS_MAX_SEG)
+  int tiles_per_row;          // ceil(Wo / seg)
   int num_segments;           // batch * Ho * tiles_per_row
   int cblocks, cb_per_unit, cb_groups;
   int ndy, dy_groups;         // filter rows per CTA (3 or 1)
@@ -242,16 +247,16 @@ template <int CB>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_strip_kernel(const __grid_constant__ WgradStripParams p, const __grid_constant__ CUtensorMap tmap_dz) {
   constexpr int ROW_BYTES = CB * 2;
-  constexpr int STRIP_BYTES = WS_STRIP_ROWS * ROW_BYTES;        // multiple of 1024 for every CB
+  constexpr int STRIP_BYTES = WS_STRIP_ROWS * ROW_BYTES;        // whole swizzle periods (1024 / 512 / 256 B) for every CB
   constexpr int CHUNKS = CB / 8;                                // 16-byte chunks per strip row
   constexpr int ROWS_PER_PASS = WG_PRODUCER_THREADS / CHUNKS;
-  constexpr int PASSES = (WS_STRIP_PIX + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
+  constexpr int PASSES = (WS_MAX_SEG + 2 + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
   constexpr uint32_t LAYOUT = CB == 64 ? 2u : (CB == 32 ? 4u : 6u);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* dz_tiles = smem;
-  uint8_t* x_tiles = smem + WS_DZ_STAGES * WG_DZ_STAGE_BYTES;
+  uint8_t* x_tiles = smem + WS_DZ_STAGES * WS_DZ_STAGE_MAX;
   uint64_t* x_full = reinterpret_cast<uint64_t*>(x_tiles + WS_X_STAGES * STRIP_BYTES);
   uint64_t* x_empty = x_full + WS_X_STAGES;
   uint64_t* dz_full = x_empty + WS_X_STAGES;
@@ -274,6 +279,9 @@ conv_wgrad_strip_kernel(const __grid_constant__ WgradStripParams p, const __grid
   const int seg_end = min(p.num_segments, seg_begin + p.segs_per_split);
   const int nseg = max(seg_end - seg_begin, 0);
   const bool two_halves = p.Cout - co_tile * 128 > 64;          // second 64-channel dZ block carries data
+  const int strip_pix = p.seg + 2;                              // input pixels feeding one segment of a 3-tap row
+  const uint32_t dz_sub = static_cast<uint32_t>(p.seg) * 128u;  // bytes of one 64-channel dZ block (multiple of 1024)
+  const int ksteps = p.seg >> 4;
   const GatherGeom& g = p.g;
 
   if (tid == 0) {
@@ -306,11 +314,11 @@ conv_wgrad_strip_kernel(const __grid_constant__ WgradStripParams p, const __grid
       const int yrow = seg / p.tiles_per_row;            // b * Ho + y
       const int img = yrow / g.Ho;
       const int y = yrow - img * g.Ho;
-      const int x0 = xseg * 128;
+      const int x0 = xseg * p.seg;
       uint32_t* xo = s_xoff + (i & 1) * WS_XOFF_WORDS;
       if (tid < WS_STRIP_ROWS) {
         int vx = x0 - g.pad_l + tid;
-        bool ok = tid < WS_STRIP_PIX;
+        bool ok = tid < strip_pix;
         if (g.pad_mode == FP_PAD_REFLECT) vx = vx < 0 ? -vx : (vx >= g.Win ? 2 * g.Win - 2 - vx : vx);
         ok = ok && static_cast<unsigned>(vx) < static_cast<unsigned>(g.Win);
         xo[tid] = ok ? static_cast<uint32_t>((g.up0 ? vx >> 1 : vx) * g.C0) : 0xFFFFFFFFu;
@@ -327,10 +335,10 @@ conv_wgrad_strip_kernel(const __grid_constant__ WgradStripParams p, const __grid
       if (tid == 0) {
         const int ds = i % WS_DZ_STAGES;
         mbar_wait(&dz_empty[ds], ((i / WS_DZ_STAGES) & 1) ^ 1, 30);
-        mbar_arrive_expect_tx(&dz_full[ds], two_halves ? WG_DZ_STAGE_BYTES : WG_SUBTILE);
-        tma_load_3d(dz_u32 + ds * WG_DZ_STAGE_BYTES, &tmap_dz, &dz_full[ds], co_tile * 128, x0, yrow);
+        mbar_arrive_expect_tx(&dz_full[ds], two_halves ? 2 * dz_sub : dz_sub);
+        tma_load_3d(dz_u32 + ds * WS_DZ_STAGE_MAX, &tmap_dz, &dz_full[ds], co_tile * 128, x0, yrow);
         if (two_halves)
-          tma_load_3d(dz_u32 + ds * WG_DZ_STAGE_BYTES + WG_SUBTILE, &tmap_dz, &dz_full[ds], co_tile * 128 + 64, x0, yrow);
+          tma_load_3d(dz_u32 + ds * WS_DZ_STAGE_MAX + dz_sub, &tmap_dz, &dz_full[ds], co_tile * 128 + 64, x0, yrow);
       }
       for (int dyi = 0; dyi < ndy; ++dyi)
         for (int j = 0; j < ncb; ++j, ++xs) {
@@ -346,7 +354,7 @@ conv_wgrad_strip_kernel(const __grid_constant__ WgradStripParams p, const __grid
 #pragma unroll
           for (int k = 0; k < PASSES; ++k) {
             const int r = r0 + ROWS_PER_PASS * k;
-            if (r < WS_STRIP_PIX) {
+            if (r < strip_pix) {
               const uint32_t xoff = xcol[r];
               const bool ok = (rowoff != 0xFFFFFFFFu) && (xoff != 0xFFFFFFFFu);
               const uint32_t off = ok ? rowoff + xoff + cc : 0u;
@@ -366,7 +374,7 @@ conv_wgrad_strip_kernel(const __grid_constant__ WgradStripParams p, const __grid
       for (int i = 0; i < nseg; ++i) {
         const int ds = i % WS_DZ_STAGES;
         mbar_wait(&dz_full[ds], (i / WS_DZ_STAGES) & 1, 32);
-        const uint32_t a_base = smem_u32(dz_tiles) + ds * WG_DZ_STAGE_BYTES;
+        const uint32_t a_base = smem_u32(dz_tiles) + ds * WS_DZ_STAGE_MAX;
         for (int dyi = 0; dyi < ndy; ++dyi)
           for (int j = 0; j < ncb; ++j, ++xs) {
             const int s = xs % WS_X_STAGES;
@@ -377,18 +385,18 @@ conv_wgrad_strip_kernel(const __grid_constant__ WgradStripParams p, const __grid
             if (p.fuse_taps) {
               // one N = 3*CB instruction per K step: B's three MN blocks are the strip at pixel shifts 0, 1, 2 (block
               // stride LBO = one strip row), so dZ (the A operand) is read from shared memory once instead of 3 times
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {
-                const uint64_t a_desc = umma_smem_desc_sw128(a_base + ks * 2048, WG_SUBTILE, 1024);
+#pragma unroll 2
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t a_desc = umma_smem_desc_sw128(a_base + ks * 2048, dz_sub, 1024);
                 const uint64_t b_desc = umma_smem_desc(strip + ks * 16 * ROW_BYTES, ROW_BYTES, 8 * ROW_BYTES, LAYOUT);
                 umma_f16(d_tmem, a_desc, b_desc, idesc3, (i | ks) != 0 ? 1u : 0u);
               }
             } else {
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                  const uint64_t a_desc = umma_smem_desc_sw128(a_base + ks * 2048, WG_SUBTILE, 1024);
+#pragma unroll 2
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint64_t a_desc = umma_smem_desc_sw128(a_base + ks * 2048, dz_sub, 1024);
                   // B = the strip advanced by dx pixels (rows); N = CB channels = one MN block (LBO unused)
                   const uint64_t b_desc = umma_smem_desc(strip + dx * ROW_BYTES + ks * 16 * ROW_BYTES, 8 * ROW_BYTES,
                                                          8 * ROW_BYTES, LAYOUT);
@@ -441,7 +449,7 @@ conv_wgrad_strip_kernel(const __grid_constant__ WgradStripParams p, const __grid
 }
 
 struct WgradStripPlan {
-  int cb, tiles_per_row, num_segments, cblocks, cb_per_unit, cb_groups, ndy, dy_groups, co_tiles, splits, segs_per_split;
+  int cb, seg, tiles_per_row, num_segments, cblocks, cb_per_unit, cb_groups, ndy, dy_groups, co_tiles, splits, segs_per_split;
 };
 
 static int wgrad_strip_cb(const FpConvDesc* d) {
@@ -452,19 +460,31 @@ static int wgrad_strip_cb(const FpConvDesc* d) {
   return 0;
 }
 
+// segment length: split the row into the fewest segments of <= WS_MAX_SEG pixels, rounded up to the MMA's K = 16
+// (measured: 160-pixel segments beat 128 for 64-channel blocks -- fewer barrier round trips per pixel -- but not for the
+// 32/16-channel blocks that keep all three filter rows in one CTA, which stay at 128 when the row divides evenly)
+static int wgrad_strip_seg(int wo, int cb) {
+  if (cb < 64 && wo % 128 == 0) return 128;
+  const int n = (wo + WS_MAX_SEG - 1) / WS_MAX_SEG;
+  const int seg = ((wo + n - 1) / n + 15) / 16 * 16;
+  return seg < 32 ? 32 : seg;
+}
+
 static bool wgrad_strip_ok(const FpConvDesc* d) {
   const char* senv = getenv("FP_WGRAD_STRIP");
-  const int segs = (d->wo + 127) / 128;
   const int cb = wgrad_strip_cb(d);
+  const int seg = wgrad_strip_seg(d->wo, cb);
+  const int segs = (d->wo + seg - 1) / seg;
   const int cin = d->c0 + d->c1;
   return d->kh == 3 && d->kw == 3 && d->stride == 1 && d->up0 != 2 && cb != 0 && d->kpad >= 9 * cin &&
-         (cb == 64 || cin / cb <= 2) && d->wo * 100 >= segs * 128 * 80 && !(senv && atoi(senv) == 0);
+         (cb == 64 || cin / cb <= 2) && d->wo >= 64 && d->wo * 100 >= segs * seg * 80 && !(senv && atoi(senv) == 0);
 }
 
 static WgradStripPlan wgrad_strip_plan(const FpConvDesc* d) {
   WgradStripPlan w;
   w.cb = wgrad_strip_cb(d);
-  w.tiles_per_row = (d->wo + 127) / 128;
+  w.seg = wgrad_strip_seg(d->wo, w.cb);
+  w.tiles_per_row = (d->wo + w.seg - 1) / w.seg;
   w.num_segments = d->batch * d->ho * w.tiles_per_row;
   w.cblocks = (d->c0 + d->c1) / w.cb;
   const int max_cb = WS_MAX_COLS / (3 * w.cb);               // channel blocks whose 3 taps fit the accumulator budget
@@ -587,7 +607,7 @@ extern "C" int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* 
     sp.g = p.g;
     const WgradStripPlan ws = wgrad_strip_plan(d);
     sp.Cout = d->cout; sp.kpad = d->kpad; sp.cin = d->c0 + d->c1;
-    sp.tiles_per_row = ws.tiles_per_row; sp.num_segments = ws.num_segments; sp.cblocks = ws.cblocks;
+    sp.seg = ws.seg; sp.tiles_per_row = ws.tiles_per_row; sp.num_segments = ws.num_segments; sp.cblocks = ws.cblocks;
     sp.cb_per_unit = ws.cb_per_unit; sp.cb_groups = ws.cb_groups; sp.ndy = ws.ndy; sp.dy_groups = ws.dy_groups;
     sp.co_tiles = ws.co_tiles; sp.splits = ws.splits; sp.segs_per_split = ws.segs_per_split;
     sp.partial = workspace; sp.a_fmt = grad_dtype; sp.b_fmt = d->dtype;
@@ -597,7 +617,7 @@ extern "C" int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* 
     }
     CUtensorMap tmap_dz3;
     rc = make_tmap_3d_sw128(&tmap_dz3, dz, static_cast<uint64_t>(dz_ld), static_cast<uint64_t>(d->wo),
-                            static_cast<uint64_t>(d->batch) * d->ho, 64u, 128u);
+                            static_cast<uint64_t>(d->batch) * d->ho, 64u, static_cast<uint32_t>(ws.seg));
     if (rc != FP_OK) return rc;
     const int grid_s = ws.cb_groups * ws.dy_groups * ws.co_tiles * ws.splits;
     rc = ws.cb == 64 ? launch_wgrad_strip<64>(sp, tmap_dz3, grid_s, st)

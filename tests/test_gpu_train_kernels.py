@@ -176,6 +176,9 @@ def _fwd_desc(b, c0, h0, w0, up0, c1, k, stride, pad, pad_mode, cout):
     dict(c0=32, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=1, cout=32, w0=160, h0=6, b=2),      # 64-byte strip rows
     dict(c0=32, c1=32, up0=1, k=3, stride=1, pad=1, pad_mode=1, cout=2, w0=80, h0=4, b=2),
     dict(c0=16, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=0, cout=16, w0=130, h0=5, b=2),      # 32-byte strip rows
+    # weight-gradient strips with 80- and 48-pixel segments (K-flexible), 4 channel blocks in 2 groups
+    dict(c0=128, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=0, cout=128, w0=80, h0=4, b=2),
+    dict(c0=256, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=0, cout=256, w0=40, h0=3, b=2),
 ])
 def test_conv_wgrad_and_dgrad(lib, cfg):
     """Weight gradient (fp_conv_wgrad) and data gradient (fp_conv_fwd with the rotated filter) against autograd."""
