@@ -269,7 +269,7 @@ def main():
     if rank == 0:
         prof, eng.profile = eng.profile, None
         agg = {}
-        for kind, name, flops, a, b in prof:
+        for kind, name, flops, a, b, _ in prof:
             t, f, n = agg.get(kind, (0.0, 0.0, 0))
             agg[kind] = (t + a.elapsed_time(b), f + flops, n + 1)
         peaks = {}
@@ -304,6 +304,22 @@ def main():
                     'algorithmic_gflop_per_step': f_igemm / 1e9,
                     'by_kind': {k: {'ms': v[0], 'tflops': (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0), 'launches': v[2]}
                                 for k, v in agg.items()}}
+
+        # second view, the bound SURVEY §8d assigns to the fused upsample/concat/pad decoder convolutions: algorithmic
+        # HBM bytes of the decoders' forward launches (inputs once pre-upsample/pre-pad + skip + outputs + weights,
+        # 16-bit) / their summed CUDA-event time, against the measured HBM copy bandwidth
+        try:
+            dec = [x for x in prof if x[0] == 'fwd' and x[1].split('.', 1)[0] in ('mask', 'depth') and x[5] > 0]
+            t_dec = sum(x[3].elapsed_time(x[4]) for x in dec)
+            b_dec = float(sum(x[5] for x in dec))
+            hbm_peak = peaks.get('hbm_gbs', 6500.0)
+            if t_dec > 0:
+                roofline['decoder_fwd_hbm'] = {'bound': 'hbm', 'achieved': b_dec / (t_dec * 1e-3) / 1e9, 'peak': hbm_peak,
+                                               'unit': 'GB/s', 'frac': b_dec / (t_dec * 1e-3) / 1e9 / hbm_peak,
+                                               'algorithmic_gb_per_step': b_dec / 1e9, 'ms_per_step': t_dec,
+                                               'launches': len(dec)}
+        except Exception as exc:               # never lose the bench line over the secondary view
+            roofline['decoder_fwd_hbm'] = {'error': repr(exc)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.mode == 'train':

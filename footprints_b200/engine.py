@@ -69,11 +69,13 @@ class Engine:
         self._weight_key = None
         self._bufs = {}
         self.launches = 0           # kernels launched through the C ABI (bench.py reports them)
-        self.profile = None         # when a list: (kind, layer, flops, start_event, end_event) per conv launch
+        self.profile = None         # when a list: (kind, layer, flops, start_event, end_event, algorithmic_bytes) per conv launch
         self._prof_open = None
 
     # ------------------------------------------------------------------------------ instrumentation
-    def _prof(self, kind, L, m_pixels):
+    def _prof(self, kind, L, m_pixels, abytes=0):
+        """abytes: algorithmic HBM bytes of the launch (unique input elements once, pre-upsample / pre-pad,
+        the concatenated skip included, + outputs once + weights once), 0 when the caller does not track it."""
         if self.profile is None:
             return
         k_real = 147 if L.stem else L.k * L.k * (L.cin0 + L.cin1)
@@ -81,7 +83,7 @@ class Engine:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        self._prof_open = (kind, L.name, flops, e0, e1)
+        self._prof_open = (kind, L.name, flops, e0, e1, abytes)
 
     def _prof_end(self):
         if self._prof_open is not None:
@@ -213,7 +215,9 @@ class Engine:
         assert c0 == L.cin0 and d.c1 == L.cin1, (L.name, c0, d.c1, L.cin0, L.cin1)
         if src1 is not None:
             assert tuple(src1.shape[1:3]) == (hin, win), (L.name, src1.shape, hin, win)
-        self._prof('fwd', L, b * d.ho * d.wo)
+        self._prof('fwd', L, b * d.ho * d.wo,
+                   2 * (src0.numel() + (src1.numel() if src1 is not None else 0) + b * d.ho * d.wo * L.cout) +
+                   2 * L.cout * L.k * L.k * (c0 + d.c1))
         _lib.check(self.lib.fp_conv_fwd(ctypes.byref(d), _ptr(src0), _ptr(src1), _ptr(L.w_packed),
                                         _ptr(L.scale if scale is None else scale),
                                         _ptr(L.shift if shift is None else shift), _ptr(residual), _ptr(out), stream))

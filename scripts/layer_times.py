@@ -20,7 +20,7 @@ prof = tr.eng.profile; tr.eng.profile = None
 print('step ms (with event overhead)', e0.elapsed_time(e1))
 tot = {}
 rows = []
-for kind, name, flops, a, b in prof:
+for kind, name, flops, a, b, _ in prof:
     ms = a.elapsed_time(b)
     rows.append((ms, kind, name, flops / ms / 1e9))
     tot[kind] = tot.get(kind, 0) + ms
