@@ -12,7 +12,17 @@
 //   warp  8    MMA issuer: one elected lane issues 4 x tcgen05.mma (M128 x BN x K16) per stage and
 //                          tcgen05.commit's the stage back to the producers / the accumulator to the epilogue.
 //   warps 9-16 epilogue  : tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next tile's
-//                          mainloop overlaps), apply scale/shift (+residual) + activation, store NHWC.
+//                          mainloop overlaps; the buffer is released right after the TMEM reads), apply
+//                          scale/shift (+residual) + activation, store NHWC.
+//
+// Two kernels share this structure:
+//   conv_igemm_kernel<BN>           any convolution (1x1 .. 4x4, stride 1/2, transposed stride 2): per-tap gather.
+//   conv_igemm_strip_kernel<BN,CB>  3x3 stride-1 on wide rows (fp_conv_fwd picks it when >= 80 % of the 128-pixel row
+//                                   segments are real pixels): one staged 130-pixel input row segment per (dy, channel
+//                                   block) serves the three dx taps through shifted UMMA descriptors; strips by TMA
+//                                   for zero-padded single-source inputs; the filter resident in shared memory.
+// What bounds them on the thin high-resolution layers: L2->SM operand bandwidth (~20 B/clk/SM) and
+// UMMA's max(M, N)/2-cycle cost per K = 16 step -- not HBM.
 #include "fp_ptx.cuh"
 #include "fp_internal.h"
 #include "igemm_common.cuh"

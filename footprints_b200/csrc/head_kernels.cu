@@ -1,7 +1,10 @@
 // Dedicated CUDA-core kernels for the 2-channel output heads (OutConvBlock, footprints/network.py:161-183): a
 // 3x3 reflection-padded convolution Cin -> 2.  With N = 2 the tensor-core implicit GEMM wastes >98 % of every
-// MMA (and of the 128-row weight-gradient tile), so forward, data gradient and weight gradient are plain FMA
-// kernels here: memory-bound, each input pixel is re-read from L1/L2 by its 9 neighbours.
+// MMA, so forward and data gradient are plain FMA kernels here.  The default paths are the shared-memory tiled
+// head_fwd_tile_kernel / head_dgrad_tile_kernel (16 x 32 pixel tiles, 4 pixels x 16 channels per thread, FMA-issue
+// bound); the per-pixel / per-chunk kernels remain as the FP_HEAD_TILE=0 variants and for C % 16 != 0.  The weight
+// gradient of the heads runs on the tensor-core row-strip kernel (conv_wgrad.cu); head_wgrad_kernel is the CUDA-core
+// reference implementation the tests pin it against.
 #include "fp_internal.h"
 
 #include <cuda_bf16.h>
