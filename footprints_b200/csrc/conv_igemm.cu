@@ -823,6 +823,286 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
   }
 }
 
+// ==================================================================================================
+// Row-streaming variant of the strip kernel  (EXPERIMENTAL: opt-in with FP_ROWSTREAM=1, not yet validated on a GPU --
+// written at the end of round 1 after the GPU budget was spent; the default dispatch never reaches it).
+//
+// Why: on the thin layers (Cout <= 64) a tcgen05.mma costs max(M, N)/2 = 64 cycles whatever N is, and L2->SM bandwidth
+// caps the strip fills; the strip kernel stages every input row three times (once per output row that uses it) and
+// issues 9*C/16 N = Cout instructions per tile.  Here a CTA walks DOWN a column of 128-pixel segments: every input row
+// segment is staged once and, per (dx, K step), ONE instruction with N = 3*BN accumulates it into the three output
+// rows it feeds -- the B operand is [W(dy=0,dx) | W(dy=1,dx) | W(dy=2,dx)] (resident, stored in that order) and the
+// three accumulators are adjacent TMEM column blocks ordered by DEcreasing output row.  TMEM (512 columns) is split
+// in two halves of H = 256/BN row slots; a work item is H consecutive output rows of one column (H + 2 input rows,
+// i.e. 1.25x (BN=32) / 1.5x (BN=64) fills per output row instead of 3x, and 3x fewer instructions), items alternate
+// halves so that the epilogue of one item overlaps the MMAs of the next.
+//   input row j of an item (virtual row v = yc - pad_t + j, j = 0 .. H+1) feeds output rows y = yc + j - dy:
+//   dy in [max(0, j-H+1), min(2, j)];  slot(y) = H-1-(y-yc)  (so dy = 0,1,2 are increasing columns).
+//   The first instruction touching a row slot (dy = 0 block, cb = dx = k = 0) is issued alone with accumulate = 0.
+// ==================================================================================================
+struct RowStreamParams {
+  IgemmParams b;
+  int tiles_per_row;         // ceil(Wo / 128)
+  int cblocks;               // (C0 + C1) / CB
+  int x_via_tma;
+  int stages;                // strip ring depth (<= StripCfg::MAX_STAGES)
+  int w_bytes;               // resident filter bytes: 9 * cblocks * B_TILE
+  int H;                     // output rows per item = row slots per TMEM half
+  int chunks_per_col;        // ceil(Ho / H)
+  int total_items;           // batch * tiles_per_row * chunks_per_col
+};
+
+template <int BN, int CB>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_constant__ CUtensorMap tmap_w,
+                      const __grid_constant__ CUtensorMap tmap_x) {
+  using Cfg = StripCfg<BN, CB>;
+  constexpr int ROW_BYTES = Cfg::ROW_BYTES;
+  constexpr int CPR = ROW_BYTES / 16;
+  constexpr int ROWS_PER_PASS = NUM_PRODUCER_THREADS / CPR;
+  constexpr uint64_t LAYOUT = (CB == 64) ? 2ull : 4ull;
+  constexpr uint32_t SBO = 8 * ROW_BYTES;
+  constexpr int MAX_STAGES = Cfg::MAX_STAGES;
+  constexpr int SLOTS = 512 / BN;                    // row slots in TMEM (two halves of H = SLOTS / 2)
+  const int STAGES = rp.stages;
+  const int H = rp.H;
+  const IgemmParams& p = rp.b;
+  const GatherGeom& g = p.g;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* stage0 = smem;                                               // [STAGES][strip]
+  uint8_t* w_res = smem + STAGES * Cfg::A_BYTES;                        // [(dx*cblocks + cb)*3 + dy][BN][CB]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(w_res + rp.w_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* row_full = empty_bar + MAX_STAGES;                          // [SLOTS] MMA -> epilogue, one per output-row slot
+  uint64_t* row_empty = row_full + SLOTS;                               // [SLOTS] epilogue -> MMA
+  uint64_t* w_bar = row_empty + SLOTS;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* s_scale = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* s_shift = s_scale + BN;
+  uint32_t* s_xoff = reinterpret_cast<uint32_t*>(s_shift + BN);        // [2][2*STRIP_ROWS] column maps of both sources
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], rp.x_via_tma ? 1 : NUM_PRODUCER_THREADS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int q = 0; q < SLOTS; ++q) {
+      mbar_init(&row_full[q], 1);
+      mbar_init(&row_empty[q], NUM_EPI_WARPS);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_w);
+    if (rp.x_via_tma) tma_prefetch_desc(&tmap_x);
+    // resident filter, regrouped so that the three dy tiles of a (dx, cb) are adjacent: one N = 3*BN B operand
+    mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(rp.w_bytes));
+    for (int dx = 0; dx < 3; ++dx)
+      for (int cb = 0; cb < rp.cblocks; ++cb)
+        for (int dy = 0; dy < 3; ++dy)
+          tma_load_2d(smem_u32(w_res) + ((dx * rp.cblocks + cb) * 3 + dy) * Cfg::B_TILE, &tmap_w, w_bar,
+                      ((dy * 3 + dx) * rp.cblocks + cb) * CB, 0);
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_ptr_smem, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // item -> (image, row segment, first output row)
+  auto decode = [&](int item, int& img, int& x0, int& yc) {
+    const int chunk = item % rp.chunks_per_col;
+    const int t = item / rp.chunks_per_col;
+    x0 = (t % rp.tiles_per_row) * BM;
+    img = t / rp.tiles_per_row;
+    yc = chunk * H;
+  };
+
+  if (warp < NUM_PRODUCER_WARPS && rp.x_via_tma) {
+    // =============================== PRODUCER (TMA) ===============================
+    if (tid == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < rp.total_items; item += gridDim.x) {
+        int img, x0, yc;
+        decode(item, img, x0, yc);
+        for (int j = 0; j < H + 2; ++j)
+          for (int cb = 0; cb < rp.cblocks; ++cb) {
+            mbar_wait(&empty_bar[s], ph ^ 1, 41);
+            mbar_arrive_expect_tx(&full_bar[s], STRIP_PIX * ROW_BYTES);
+            tma_load_4d(smem_u32(stage0) + s * Cfg::A_BYTES, &tmap_x, &full_bar[s], cb * CB, x0 - g.pad_l,
+                        yc - g.pad_t + j, img);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+      }
+    }
+  } else if (warp < NUM_PRODUCER_WARPS) {
+    // =============================== PRODUCERS (cp.async) ===============================
+    const int c = tid % CPR;
+    const int r0 = tid / CPR;
+    int s = 0;
+    uint32_t ph = 0, it = 0;
+    for (int item = blockIdx.x; item < rp.total_items; item += gridDim.x, ++it) {
+      int img, x0, yc;
+      decode(item, img, x0, yc);
+      uint32_t* xo = s_xoff + (it & 1) * (2 * STRIP_ROWS);
+      if (tid < STRIP_ROWS) {
+        int vx = x0 - g.pad_l + tid;
+        bool ok = tid < STRIP_PIX;
+        if (g.pad_mode == FP_PAD_REFLECT) vx = vx < 0 ? -vx : (vx >= g.Win ? 2 * g.Win - 2 - vx : vx);
+        ok = ok && static_cast<unsigned>(vx) < static_cast<unsigned>(g.Win);
+        xo[tid] = ok ? static_cast<uint32_t>((g.up0 ? vx >> 1 : vx) * g.C0) : 0xFFFFFFFFu;
+        xo[STRIP_ROWS + tid] = ok ? static_cast<uint32_t>(vx * g.C1) : 0xFFFFFFFFu;
+      }
+      named_bar_sync(2, NUM_PRODUCER_THREADS);
+      for (int j = 0; j < H + 2; ++j) {
+        int vy = yc - g.pad_t + j;
+        if (g.pad_mode == FP_PAD_REFLECT) vy = vy < 0 ? -vy : (vy >= g.Hin ? 2 * g.Hin - 2 - vy : vy);
+        const bool row_ok = static_cast<unsigned>(vy) < static_cast<unsigned>(g.Hin);   // rows past a ragged item: zeros
+        const uint32_t rowoff0 = static_cast<uint32_t>(((img * g.H0 + (g.up0 ? vy >> 1 : vy)) * g.W0) * g.C0);
+        const uint32_t rowoff1 = static_cast<uint32_t>(((img * g.Hin + vy) * g.Win) * g.C1);
+        for (int cb = 0; cb < rp.cblocks; ++cb) {
+          mbar_wait(&empty_bar[s], ph ^ 1, 42);
+          const uint32_t stage = smem_u32(stage0) + s * Cfg::A_BYTES;
+          const int ch = cb * CB;
+          const bool second = ch >= g.C0;
+          const uint8_t* sbase = second ? g.src1 : g.src0;
+          const uint32_t rowoff = second ? rowoff1 : rowoff0;
+          const uint32_t* xcol = xo + (second ? STRIP_ROWS : 0);
+          const uint32_t cc = static_cast<uint32_t>(second ? ch - g.C0 : ch) + c * 8;
+#pragma unroll
+          for (int i = 0; i < (STRIP_PIX + ROWS_PER_PASS - 1) / ROWS_PER_PASS; ++i) {
+            const int r = r0 + ROWS_PER_PASS * i;
+            if (r < STRIP_PIX) {
+              const uint32_t xoff = xcol[r];
+              const bool ok = row_ok && (xoff != 0xFFFFFFFFu);
+              const uint32_t off = ok ? rowoff + xoff + cc : 0u;
+              const int sw = (CB == 64) ? (c ^ (r & 7)) : (c ^ ((r >> 1) & 3));
+              cp_async_16_zfill(stage + r * ROW_BYTES + (sw << 4), sbase + static_cast<size_t>(off) * 2, ok);
+            }
+          }
+          cp_async_mbar_arrive_noinc(&full_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // =============================== MMA ISSUER ===============================
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_f16(BM, BN, p.fmt, p.w_fmt, 0, 0);
+      const uint32_t idesc2 = umma_idesc_f16(BM, 2 * BN, p.fmt, p.w_fmt, 0, 0);
+      const uint32_t idesc3 = umma_idesc_f16(BM, 3 * BN, p.fmt, p.w_fmt, 0, 0);
+      constexpr uint32_t DESC_HI = (SBO >> 4) | (1u << 14) | (static_cast<uint32_t>(LAYOUT) << 29);
+      auto mk_desc = [](uint32_t lo) -> uint64_t { return (static_cast<uint64_t>(DESC_HI) << 32) | lo; };
+      const uint32_t stage0_lo = ((smem_u32(stage0) >> 4) & 0x3FFF) | (1u << 16);
+      const uint32_t wres_lo = ((smem_u32(w_res) >> 4) & 0x3FFF) | (1u << 16);
+      constexpr uint32_t BT = Cfg::B_TILE >> 4;
+      int s = 0;
+      uint32_t ph = 0, it = 0;
+      mbar_wait(w_bar, 0, 43);
+      for (int item = blockIdx.x; item < rp.total_items; item += gridDim.x, ++it) {
+        const uint32_t half = it & 1;
+        const uint32_t use_par = (it >> 1) & 1;            // parity of this half's use count
+        for (int j = 0; j < H + 2; ++j) {
+          const int dy_lo = j > H - 1 ? j - (H - 1) : 0;
+          const int dy_hi = j < 2 ? j : 2;
+          const int ndy = dy_hi - dy_lo + 1;
+          const int q_hi = (H - 1) - (j - dy_lo);          // slot of the dy_lo block's output row
+          const uint32_t d_col = tmem_base + (half * H + q_hi) * BN;
+          if (dy_lo == 0) {                                // first touch of this row slot in this item
+            mbar_wait(&row_empty[half * H + q_hi], use_par ^ 1, 44);
+            tcgen05_fence_after();
+          }
+          const uint32_t idesc_n = ndy == 3 ? idesc3 : (ndy == 2 ? idesc2 : idesc1);
+          const uint32_t idesc_rest = ndy == 3 ? idesc2 : idesc1;   // the dy >= 1 blocks when dy = 0 is split off
+          for (int cb = 0; cb < rp.cblocks; ++cb) {
+            mbar_wait(&full_bar[s], ph, 45);
+            tcgen05_fence_after();
+            const uint32_t a_lo = stage0_lo + static_cast<uint32_t>(s) * (Cfg::A_BYTES >> 4);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const uint32_t b_lo = wres_lo + ((dx * rp.cblocks + cb) * 3 + dy_lo) * BT;
+#pragma unroll
+              for (int k = 0; k < CB / 16; ++k) {
+                const uint64_t a_desc = mk_desc(a_lo + dx * (ROW_BYTES >> 4) + 2 * k);
+                if (dy_lo == 0 && cb == 0 && dx == 0 && k == 0) {
+                  umma_f16(d_col, a_desc, mk_desc(b_lo), idesc1, 0u);                       // opens the row's accumulator
+                  if (ndy > 1) umma_f16(d_col + BN, a_desc, mk_desc(b_lo + BT), idesc_rest, 1u);
+                } else {
+                  umma_f16(d_col, a_desc, mk_desc(b_lo + 2 * k), idesc_n, 1u);
+                }
+              }
+            }
+            umma_commit(&empty_bar[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+          if (j >= 2) umma_commit(&row_full[half * H + (H - 1) - (j - 2)]);   // output row yc + j - 2 is complete
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== EPILOGUE ===============================
+    const int q = warp & 3;
+    const int hf = (warp - EPI_FIRST_WARP) >> 2;
+    const int row = q * 32 + lane;
+    const int e = tid - EPI_FIRST_WARP * 32;
+    constexpr int COLS_PER_HALF = BN / 2;
+    const int col_begin = hf * COLS_PER_HALF;
+    for (int j = e; j < BN; j += NUM_EPI_THREADS) {
+      s_scale[j] = (p.scale != nullptr && j < p.N) ? p.scale[j] : 1.f;
+      s_shift[j] = (p.shift != nullptr && j < p.N) ? p.shift[j] : 0.f;
+    }
+    named_bar_sync(1, NUM_EPI_THREADS);
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < rp.total_items; item += gridDim.x, ++it) {
+      int img, x0, yc;
+      decode(item, img, x0, yc);
+      const uint32_t half = it & 1;
+      const uint32_t use_par = (it >> 1) & 1;
+      for (int r = 0; r < H; ++r) {
+        const int slot = half * H + (H - 1 - r);
+        const int y = yc + r;
+        mbar_wait<32>(&row_full[slot], use_par, 46);
+        tcgen05_fence_after();
+        const int m = (img * g.Ho + y) * g.Wo + x0 + row;
+        const bool m_ok = (x0 + row) < g.Wo && y < g.Ho;
+        const uint32_t tbase = tmem_base + slot * BN + (static_cast<uint32_t>(q * 32) << 16);
+#define FP_EPI(A, F) epilogue_cols<A, F, COLS_PER_HALF>(p, tbase, col_begin, 0, m, m_ok, s_scale, s_shift, &row_empty[slot], lane)
+        if (p.fmt == FP_BF16) {
+          switch (p.act) {
+            case FP_ACT_RELU: FP_EPI(FP_ACT_RELU, FP_BF16); break;
+            case FP_ACT_ELU: FP_EPI(FP_ACT_ELU, FP_BF16); break;
+            case FP_ACT_SIGMOID: FP_EPI(FP_ACT_SIGMOID, FP_BF16); break;
+            default: FP_EPI(FP_ACT_NONE, FP_BF16); break;
+          }
+        } else {
+          switch (p.act) {
+            case FP_ACT_RELU: FP_EPI(FP_ACT_RELU, FP_F16); break;
+            case FP_ACT_ELU: FP_EPI(FP_ACT_ELU, FP_F16); break;
+            case FP_ACT_SIGMOID: FP_EPI(FP_ACT_SIGMOID, FP_F16); break;
+            default: FP_EPI(FP_ACT_NONE, FP_F16); break;
+          }
+        }
+#undef FP_EPI
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // minimum fraction (percent) of the 128-pixel row segments that must be real output pixels (FP_STRIP_MINEFF)
 static int strip_min_eff() {
   static int v = -1;
@@ -861,6 +1141,40 @@ static int launch_strip(const StripParams& sp_in, const CUtensorMap& tmap, const
   kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(sp, tmap, tmap_x);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "conv_igemm_strip launch (BN=%d): %s", BN, cudaGetErrorString(e));
+  return FP_OK;
+}
+
+// Row-streaming launch (experimental, FP_ROWSTREAM=1): returns FP_ERR_UNSUPPORTED when the filter + 3 strip stages do
+// not fit, so that the caller falls back to the strip kernel.
+template <int BN, int CB>
+static int launch_rowstream(const StripParams& sp, const CUtensorMap& tmap, const CUtensorMap& tmap_x, cudaStream_t stream) {
+  using Cfg = StripCfg<BN, CB>;
+  constexpr int SLOTS = 512 / BN;
+  constexpr int RS_FIXED = 1024 + (2 * Cfg::MAX_STAGES + 2 * SLOTS + 1) * 8 + 16 + 2 * BN * 4 + 2 * 2 * STRIP_ROWS * 4;
+  RowStreamParams rp{};
+  rp.b = sp.b;
+  rp.tiles_per_row = sp.tiles_per_row;
+  rp.cblocks = sp.cblocks;
+  rp.x_via_tma = sp.x_via_tma;
+  rp.w_bytes = 9 * sp.cblocks * Cfg::B_TILE;
+  const int room = Cfg::SMEM_MAX - RS_FIXED - rp.w_bytes;
+  if (sp.b.n_tiles != 1 || room < 3 * Cfg::A_BYTES) return FP_ERR_UNSUPPORTED;
+  rp.stages = room / Cfg::A_BYTES < Cfg::MAX_STAGES ? room / Cfg::A_BYTES : Cfg::MAX_STAGES;
+  rp.H = SLOTS / 2;
+  rp.chunks_per_col = (sp.b.g.Ho + rp.H - 1) / rp.H;
+  rp.total_items = sp.b.g.M / sp.b.g.HoWo * sp.tiles_per_row * rp.chunks_per_col;
+  static bool attr_set = false;
+  auto kern = conv_rowstream_kernel<BN, CB>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_MAX);
+    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(rowstream): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int smem_bytes = RS_FIXED + rp.stages * Cfg::A_BYTES + rp.w_bytes;
+  const int grid = rp.total_items < num_sms() ? rp.total_items : num_sms();
+  kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(rp, tmap, tmap_x);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "conv_rowstream launch (BN=%d): %s", BN, cudaGetErrorString(e));
   return FP_OK;
 }
 
@@ -983,6 +1297,17 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
                             static_cast<uint32_t>(STRIP_PIX), cb * 2);
         if (rc != FP_OK) return rc;
         sp.x_via_tma = 1;
+      }
+      {   // experimental row-streaming kernel (opt-in; see conv_rowstream_kernel): Cout tile <= 64, single channel tile
+        const char* renv = getenv("FP_ROWSTREAM");
+        if (renv && atoi(renv) == 1 && d->bn <= 64 && sp.b.n_tiles == 1) {
+          int rrc = FP_ERR_UNSUPPORTED;
+          if (cb == 64 && d->bn == 32) rrc = launch_rowstream<32, 64>(sp, tmap_s, tmap_x, st);
+          else if (cb == 64 && d->bn == 64) rrc = launch_rowstream<64, 64>(sp, tmap_s, tmap_x, st);
+          else if (cb == 32 && d->bn == 32) rrc = launch_rowstream<32, 32>(sp, tmap_s, tmap_x, st);
+          else if (cb == 32 && d->bn == 64) rrc = launch_rowstream<64, 32>(sp, tmap_s, tmap_x, st);
+          if (rrc != FP_ERR_UNSUPPORTED) return rrc;
+        }
       }
       if (cb == 64) {
         switch (d->bn) {

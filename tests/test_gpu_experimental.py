@@ -1,0 +1,81 @@
+"""Opt-in GPU tests of kernels that are compiled in but NOT dispatched by default (they were written after the round's
+GPU budget was spent and have not run on hardware yet).  Enable with FP_TEST_EXPERIMENTAL=1:
+
+    FP_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -q -m gpu
+
+* conv_rowstream_kernel (FP_ROWSTREAM=1): row-streaming 3x3 convolution, one N = 3*Cout tcgen05.mma per (input row,
+  dx, K step); compared against the default strip kernel and against torch's conv2d on the same 16-bit operands.
+"""
+import ctypes
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from footprints_b200 import _lib
+from footprints_b200._lib import FpConvDesc
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get('FP_TEST_EXPERIMENTAL') != '1',
+                                 reason='experimental kernels: set FP_TEST_EXPERIMENTAL=1')]
+BF = 1
+DT = torch.bfloat16
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(c0=32, c1=0, up0=0, pad=1, pad_mode=1, cout=32, h=20, w=256, b=2),     # reflect, cp.async strips, BN 32 / CB 32
+    dict(c0=32, c1=0, up0=0, pad=2, pad_mode=0, cout=64, h=19, w=300, b=2),     # full correlation (dgrad), TMA strips
+    dict(c0=64, c1=0, up0=1, pad=1, pad_mode=1, cout=32, h=10, w=128, b=2),     # upsampled source, BN 32 / CB 64
+    dict(c0=64, c1=64, up0=1, pad=1, pad_mode=1, cout=64, h=9, w=80, b=1),      # upsample + concat, 2 channel blocks
+    dict(c0=64, c1=0, up0=0, pad=2, pad_mode=0, cout=64, h=13, w=130, b=3),     # ragged last item (Ho % H != 0)
+])
+def test_rowstream_matches_strip_kernel_and_torch(cfg):
+    lib = _lib.load()
+    _lib.require_device()
+    g = torch.Generator().manual_seed(11)
+    b, h0, w0 = cfg['b'], cfg['h'], cfg['w']
+    c0, c1, cout, pad = cfg['c0'], cfg['c1'], cfg['cout'], cfg['pad']
+    hin, win = (2 * h0, 2 * w0) if cfg['up0'] else (h0, w0)
+    cin = c0 + c1
+    x0 = (torch.randn(b, c0, h0, w0, generator=g)).to(DT).float().cuda()
+    x1 = (torch.randn(b, c1, hin, win, generator=g)).to(DT).float().cuda() if c1 else None
+    wgt = (torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5).to(DT).float().cuda()
+    bias = (torch.randn(cout, generator=g) * 0.1).cuda()
+    xin = F.interpolate(x0, scale_factor=2, mode='nearest') if cfg['up0'] else x0
+    if x1 is not None:
+        xin = torch.cat([xin, x1], 1)
+    if cfg['pad_mode'] == 1:
+        ref = F.conv2d(F.pad(xin, (1, 1, 1, 1), mode='reflect'), wgt, bias)
+    else:
+        ref = F.conv2d(xin, wgt, bias, padding=pad)
+    ref = F.elu(ref)
+    ho, wo = ref.shape[2], ref.shape[3]
+    bn_t = 32 if cout <= 32 else 64
+    kpad = (9 * cin + 63) // 64 * 64
+    wp = torch.empty(bn_t, kpad, dtype=DT, device='cuda')
+    _lib.check(lib.fp_pack_conv_weight(P(wgt), cout, cin, 3, 3, cin, bn_t, kpad, BF, 0, P(wp), None))
+    d = FpConvDesc(batch=b, c0=c0, h0=h0, w0=w0, up0=cfg['up0'], c1=c1, kh=3, kw=3, stride=1, pad_t=pad, pad_l=pad,
+                   pad_mode=cfg['pad_mode'], ho=ho, wo=wo, cout=cout, kpad=kpad, npad=bn_t, bn=bn_t, act=2, dtype=BF,
+                   out_f32=0, out_ld=cout, res_ld=0, b_via_tma=1, w_dtype_plus1=0)
+    s0 = x0.permute(0, 2, 3, 1).contiguous().to(DT)
+    s1 = x1.permute(0, 2, 3, 1).contiguous().to(DT) if x1 is not None else None
+    ones = torch.ones(cout, device='cuda')
+    outs = {}
+    for mode in ('0', '1'):
+        os.environ['FP_ROWSTREAM'] = mode
+        try:
+            y = torch.full((b, ho, wo, cout), float('nan'), dtype=DT, device='cuda')
+            _lib.check(lib.fp_conv_fwd(ctypes.byref(d), P(s0), P(s1), P(wp), P(ones), P(bias), None, P(y), None))
+            torch.cuda.synchronize()
+            outs[mode] = y.float().permute(0, 3, 1, 2)
+        finally:
+            os.environ.pop('FP_ROWSTREAM', None)
+    tol = 2e-2 * ref.abs().max().item()
+    assert (outs['0'] - ref).abs().max().item() <= tol
+    assert (outs['1'] - ref).abs().max().item() <= tol
+    assert (outs['1'] - outs['0']).abs().max().item() <= tol
