@@ -5,6 +5,8 @@ GPU budget was spent and have not run on hardware yet).  Enable with FP_TEST_EXP
 
 * conv_rowstream_kernel (FP_ROWSTREAM=1): row-streaming 3x3 convolution, one N = 3*Cout tcgen05.mma per (input row,
   dx, K step); compared against the default strip kernel and against torch's conv2d on the same 16-bit operands.
+* the non-default dispatch variants selected by environment variables: the same convolution must
+  come out of every variant.
 """
 import ctypes
 import os
@@ -79,3 +81,46 @@ def test_rowstream_matches_strip_kernel_and_torch(cfg):
     assert (outs['0'] - ref).abs().max().item() <= tol
     assert (outs['1'] - ref).abs().max().item() <= tol
     assert (outs['1'] - outs['0']).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize('env', [{'FP_STRIP': '0'}, {'FP_STRIP_TMA': '0'}, {'FP_STRIP_WRES': '0'},
+                                 {'FP_STRIP_TMA': '0', 'FP_STRIP_WRES': '0'}])
+@pytest.mark.parametrize('cfg', [
+    dict(c0=32, c1=0, up0=0, pad=2, pad_mode=0, cout=32, h=12, w=200, b=2),
+    dict(c0=64, c1=64, up0=1, pad=1, pad_mode=1, cout=64, h=6, w=80, b=2),
+])
+def test_dispatch_variants_agree(cfg, env):
+    lib = _lib.load()
+    _lib.require_device()
+    g = torch.Generator().manual_seed(12)
+    b, h0, w0 = cfg['b'], cfg['h'], cfg['w']
+    c0, c1, cout, pad = cfg['c0'], cfg['c1'], cfg['cout'], cfg['pad']
+    hin, win = (2 * h0, 2 * w0) if cfg['up0'] else (h0, w0)
+    cin = c0 + c1
+    s0 = torch.randn(b, h0, w0, c0, generator=g).to(DT).cuda()
+    s1 = torch.randn(b, hin, win, c1, generator=g).to(DT).cuda() if c1 else None
+    wgt = (torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5).cuda()
+    ho, wo = hin + 2 * pad - 2, win + 2 * pad - 2
+    bn_t = 32 if cout <= 32 else 64
+    kpad = (9 * cin + 63) // 64 * 64
+    wp = torch.empty(bn_t, kpad, dtype=DT, device='cuda')
+    _lib.check(lib.fp_pack_conv_weight(P(wgt), cout, cin, 3, 3, cin, bn_t, kpad, BF, 0, P(wp), None))
+    d = FpConvDesc(batch=b, c0=c0, h0=h0, w0=w0, up0=cfg['up0'], c1=c1, kh=3, kw=3, stride=1, pad_t=pad, pad_l=pad,
+                   pad_mode=cfg['pad_mode'], ho=ho, wo=wo, cout=cout, kpad=kpad, npad=bn_t, bn=bn_t, act=0, dtype=BF,
+                   out_f32=0, out_ld=cout, res_ld=0, b_via_tma=1, w_dtype_plus1=0)
+
+    def run():
+        y = torch.full((b, ho, wo, cout), float('nan'), dtype=DT, device='cuda')
+        _lib.check(lib.fp_conv_fwd(ctypes.byref(d), P(s0), P(s1), P(wp), None, None, None, P(y), None))
+        torch.cuda.synchronize()
+        return y.float()
+
+    base = run()
+    os.environ.update(env)
+    try:
+        var = run()
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+    assert torch.isfinite(var).all()
+    assert (var - base).abs().max().item() <= 2e-2 * base.abs().max().item()
