@@ -448,6 +448,247 @@ conv_wgrad_strip_kernel(const __grid_constant__ WgradStripParams p, const __grid
   }
 }
 
+// ==================================================================================================
+// Rolling, row-paired variant  (EXPERIMENTAL: opt-in with FP_WGRAD_ROLL=1, written after round 1's GPU budget was
+// spent, never run on hardware; the default dispatch does not reach it.  Control logic pinned on the CPU by
+// tests/test_wgrad_roll_emulation.py.)
+//
+// For Cout <= 64 the strip kernel above wastes half of every instruction's M = 128 and stages each input row and each dZ
+// row three times (once per filter row).  Here a CTA walks DOWN a column of row segments of one image: every input row
+// segment X[v] and every dZ row segment is staged once, and per K step (16 pixels) two instructions are issued:
+//   pair  : A = [dZ[y-1] (64 ch) ; dZ[y] (64 ch)]  (two adjacent dZ ring slots, LBO = slot stride), B = X[v], 3 taps fused
+//           -> TMEM lanes 0-63 += filter row dy = 1, lanes 64-127 += filter row dy = 0         (y = v + pad)
+//   single: A = [dZ[y-2] ; (ignored)], same B  -> lanes 0-63 of a second accumulator block += filter row dy = 2
+// The dZ ring has 4 slots plus a 5th that duplicates every row with y % 4 == 0, so "slot(y-1) + 1" always holds row y.
+// Rows outside the image arrive as zeros (4-D TMA box, out-of-bounds fill), so no instruction is conditional.
+// ==================================================================================================
+constexpr int WR_DZ_SLOTS = 5;
+constexpr int WR_BAR_BYTES = 256;
+
+template <int CB> constexpr int wr_x_stages() { return CB == 64 ? 5 : 6; }
+template <int CB> constexpr int wr_smem_bytes() {
+  return 1024 + WR_DZ_SLOTS * WS_DZ_SUB_MAX + wr_x_stages<CB>() * WS_STRIP_ROWS * CB * 2 + WR_BAR_BYTES + 16 +
+         2 * WS_XOFF_WORDS * 4;
+}
+
+struct WgradRollParams {
+  GatherGeom g;
+  int Cout, kpad, cin;
+  int seg, tiles_per_row;
+  int num_cols;               // batch * tiles_per_row columns of row segments
+  int cblocks, cb_per_unit, cb_groups;
+  int splits, cols_per_split;
+  float* partial;             // [splits][64][kpad]
+  int a_fmt, b_fmt;
+};
+
+template <int CB>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_roll_kernel(const __grid_constant__ WgradRollParams p, const __grid_constant__ CUtensorMap tmap_dz) {
+  constexpr int ROW_BYTES = CB * 2;
+  constexpr int STRIP_BYTES = WS_STRIP_ROWS * ROW_BYTES;
+  constexpr int CHUNKS = CB / 8;
+  constexpr int ROWS_PER_PASS = WG_PRODUCER_THREADS / CHUNKS;
+  constexpr int PASSES = (WS_MAX_SEG + 2 + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
+  constexpr uint32_t LAYOUT = CB == 64 ? 2u : (CB == 32 ? 4u : 6u);
+  constexpr int X_STAGES = wr_x_stages<CB>();
+  constexpr uint32_t SINGLE_COL = 256;                          // accumulator block of filter row dy = 2
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* dz_ring = smem;                                      // [5][seg px][64 ch], slot stride WS_DZ_SUB_MAX
+  uint8_t* x_tiles = smem + WR_DZ_SLOTS * WS_DZ_SUB_MAX;
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(x_tiles + X_STAGES * STRIP_BYTES);
+  uint64_t* x_empty = x_full + X_STAGES;
+  uint64_t* dz_full = x_empty + X_STAGES;
+  uint64_t* dz_empty = dz_full + WR_DZ_SLOTS;
+  uint64_t* done_bar = dz_empty + WR_DZ_SLOTS;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(x_full) + WR_BAR_BYTES);
+  uint32_t* s_xoff = tmem_ptr_smem + 4;                         // [2][2 * WS_STRIP_ROWS] column maps of both sources
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cbg = blockIdx.x % p.cb_groups;
+  const int split = blockIdx.x / p.cb_groups;
+  const int cb0 = cbg * p.cb_per_unit;
+  const int ncb = min(p.cb_per_unit, p.cblocks - cb0);
+  const int col_begin = split * p.cols_per_split;
+  const int col_end = min(p.num_cols, col_begin + p.cols_per_split);
+  const int strip_pix = p.seg + 2;
+  const uint32_t dz_bytes = static_cast<uint32_t>(p.seg) * 128u;
+  const int ksteps = p.seg >> 4;
+  const GatherGeom& g = p.g;
+
+  if (tid == 0) {
+    for (int s = 0; s < X_STAGES; ++s) {
+      mbar_init(&x_full[s], WG_PRODUCER_THREADS);
+      mbar_init(&x_empty[s], 1);
+    }
+    for (int s = 0; s < WR_DZ_SLOTS; ++s) {
+      mbar_init(&dz_full[s], 1);
+      mbar_init(&dz_empty[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_dz);
+  }
+  if (warp == WG_MMA_WARP) tmem_alloc(tmem_ptr_smem, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < WG_PRODUCER_WARPS) {
+    // =============================== PRODUCERS ===============================
+    const int c = tid % CHUNKS, r0 = tid / CHUNKS;
+    const uint32_t x_u32 = smem_u32(x_tiles), dz_u32 = smem_u32(dz_ring);
+    uint32_t xs = 0, ci = 0;
+    uint32_t empty_ph = 0;                                       // bit s: phase of dz_empty[s] this thread waits for next
+    for (int col = col_begin; col < col_end; ++col, ++ci) {
+      const int img = col / p.tiles_per_row;
+      const int x0 = (col - img * p.tiles_per_row) * p.seg;
+      uint32_t* xo = s_xoff + (ci & 1) * (2 * WS_STRIP_ROWS);
+      if (tid < WS_STRIP_ROWS) {
+        int vx = x0 - g.pad_l + tid;
+        bool ok = tid < strip_pix;
+        if (g.pad_mode == FP_PAD_REFLECT) vx = vx < 0 ? -vx : (vx >= g.Win ? 2 * g.Win - 2 - vx : vx);
+        ok = ok && static_cast<unsigned>(vx) < static_cast<unsigned>(g.Win);
+        xo[tid] = ok ? static_cast<uint32_t>((g.up0 ? vx >> 1 : vx) * g.C0) : 0xFFFFFFFFu;
+        xo[WS_STRIP_ROWS + tid] = ok ? static_cast<uint32_t>(vx * g.C1) : 0xFFFFFFFFu;
+      }
+      named_bar_sync(2, WG_PRODUCER_THREADS);
+      for (int y = -2; y < g.Ho + 2; ++y) {
+        if (tid == 0) {
+          // dZ row y (zeros outside the image) -> ring slot y mod 4, and a copy in slot 4 when y % 4 == 0
+          const int slot = (y + 4) & 3;
+          mbar_wait(&dz_empty[slot], ((empty_ph >> slot) & 1) ^ 1, 50);
+          empty_ph ^= 1u << slot;
+          mbar_arrive_expect_tx(&dz_full[slot], dz_bytes);
+          tma_load_4d(dz_u32 + slot * WS_DZ_SUB_MAX, &tmap_dz, &dz_full[slot], 0, x0, y, img);
+          if (slot == 0 && y >= 0) {
+            mbar_wait(&dz_empty[4], ((empty_ph >> 4) & 1) ^ 1, 51);
+            empty_ph ^= 1u << 4;
+            mbar_arrive_expect_tx(&dz_full[4], dz_bytes);
+            tma_load_4d(dz_u32 + 4 * WS_DZ_SUB_MAX, &tmap_dz, &dz_full[4], 0, x0, y, img);
+          }
+        }
+        if (y < 0) continue;                                     // rows -2, -1 only prime the ring with zeros
+        int vy = y - g.pad_t;
+        if (g.pad_mode == FP_PAD_REFLECT) vy = vy < 0 ? -vy : (vy >= g.Hin ? 2 * g.Hin - 2 - vy : vy);
+        const bool row_ok = static_cast<unsigned>(vy) < static_cast<unsigned>(g.Hin);
+        const uint32_t rowoff0 = static_cast<uint32_t>(((img * g.H0 + (g.up0 ? vy >> 1 : vy)) * g.W0) * g.C0);
+        const uint32_t rowoff1 = static_cast<uint32_t>(((img * g.Hin + vy) * g.Win) * g.C1);
+        for (int j = 0; j < ncb; ++j, ++xs) {
+          const int s = xs % X_STAGES;
+          mbar_wait(&x_empty[s], ((xs / X_STAGES) & 1) ^ 1, 52);
+          const uint32_t stage = x_u32 + s * STRIP_BYTES;
+          const int ch = (cb0 + j) * CB;
+          const bool second = ch >= g.C0;
+          const uint8_t* sbase = second ? g.src1 : g.src0;
+          const uint32_t rowoff = second ? rowoff1 : rowoff0;
+          const uint32_t* xcol = xo + (second ? WS_STRIP_ROWS : 0);
+          const uint32_t cc = static_cast<uint32_t>(second ? ch - g.C0 : ch) + c * 8;
+#pragma unroll
+          for (int k = 0; k < PASSES; ++k) {
+            const int r = r0 + ROWS_PER_PASS * k;
+            if (r < strip_pix) {
+              const uint32_t xoff = xcol[r];
+              const bool ok = row_ok && (xoff != 0xFFFFFFFFu);
+              const uint32_t off = ok ? rowoff + xoff + cc : 0u;
+              const int sw = CB == 64 ? (r & 7) : (CB == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
+              cp_async_16_zfill(stage + r * ROW_BYTES + ((c ^ sw) << 4), sbase + static_cast<size_t>(off) * 2, ok);
+            }
+          }
+          cp_async_mbar_arrive_noinc(&x_full[s]);
+        }
+      }
+    }
+  } else if (warp == WG_MMA_WARP) {
+    // =============================== MMA ISSUER ===============================
+    if (lane == 0) {
+      const uint32_t idesc3 = umma_idesc_f16(128, 3 * CB, p.a_fmt, p.b_fmt, 1, 1);
+      const uint32_t ring_u32 = smem_u32(dz_ring);
+      uint32_t xs = 0;
+      uint32_t full_ph = 0;                                      // bit s: phase of dz_full[s] to wait for next
+      bool first = true;
+      auto wait_full = [&](int slot) {
+        mbar_wait(&dz_full[slot], (full_ph >> slot) & 1, 53);
+        full_ph ^= 1u << slot;
+      };
+      for (int col = col_begin; col < col_end; ++col) {
+        for (int y = 0; y < g.Ho + 2; ++y) {
+          if (y == 0) { wait_full(2); wait_full(3); }            // rows -2, -1 (slots 2, 3)
+          const int s_new = y & 3;
+          wait_full(s_new);
+          if (s_new == 0) wait_full(4);
+          const uint32_t a_pair = ring_u32 + ((y + 3) & 3) * WS_DZ_SUB_MAX;      // slot(y-1); its successor holds row y
+          const uint32_t a_single = ring_u32 + ((y + 2) & 3) * WS_DZ_SUB_MAX;    // slot(y-2)
+          for (int j = 0; j < ncb; ++j, ++xs) {
+            const int s = xs % X_STAGES;
+            mbar_wait(&x_full[s], (xs / X_STAGES) & 1, 54);
+            tcgen05_fence_after();
+            const uint32_t strip = smem_u32(x_tiles) + s * STRIP_BYTES;
+            const uint32_t d_pair = tmem_base + j * 3 * CB;
+#pragma unroll 2
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t b_desc = umma_smem_desc(strip + ks * 16 * ROW_BYTES, ROW_BYTES, 8 * ROW_BYTES, LAYOUT);
+              const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+              umma_f16(d_pair, umma_smem_desc_sw128(a_pair + ks * 2048, WS_DZ_SUB_MAX, 1024), b_desc, idesc3, acc);
+              umma_f16(d_pair + SINGLE_COL, umma_smem_desc_sw128(a_single + ks * 2048, WS_DZ_SUB_MAX, 1024), b_desc, idesc3,
+                       acc);
+            }
+            umma_commit(&x_empty[s]);
+          }
+          first = false;
+          // row y-2 is no longer referenced (it was the "single" row); the duplicate slot is free after its pair
+          umma_commit(&dz_empty[(y + 2) & 3]);
+          if (s_new == 0) umma_commit(&dz_empty[4]);
+        }
+        // rows Ho, Ho+1 (zero rows) still occupy their slots: hand them back for the next column
+        umma_commit(&dz_empty[g.Ho & 3]);
+        umma_commit(&dz_empty[(g.Ho + 1) & 3]);
+      }
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else {
+    // =============================== EPILOGUE (once) ===============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                               // TMEM lane: 0-63 -> (dy 1 | dy 2), 64-127 -> dy 0
+    mbar_wait<256>(done_bar, 0, 55);
+    tcgen05_fence_after();
+    const int co = row & 63;
+    const bool row_ok = co < p.Cout;                             // (the host never creates an empty split)
+    float* dst_row = p.partial + (static_cast<size_t>(split) * 64 + co) * p.kpad;
+    for (int blk = 0; blk < 2; ++blk) {                          // 0: pair accumulator, 1: single accumulator
+      if (blk == 1 && row >= 64) break;                          // warp-uniform (q >= 2): lanes 64-127 of "single" are unused
+      const int dy = blk == 1 ? 2 : (row < 64 ? 1 : 0);
+      for (int j = 0; j < ncb; ++j)
+        for (int dx = 0; dx < 3; ++dx) {
+          float* dst = dst_row + (dy * 3 + dx) * p.cin + (cb0 + j) * CB;
+#pragma unroll 1
+          for (int cidx = 0; cidx < CB; cidx += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_base + blk * SINGLE_COL + (j * 3 + dx) * CB + cidx + (static_cast<uint32_t>(q * 32) << 16), v);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int x = 0; x < 4; ++x)
+                *reinterpret_cast<float4*>(dst + cidx + 4 * x) =
+                    make_float4(__uint_as_float(v[4 * x]), __uint_as_float(v[4 * x + 1]), __uint_as_float(v[4 * x + 2]),
+                                __uint_as_float(v[4 * x + 3]));
+            }
+          }
+        }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == WG_MMA_WARP) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 struct WgradStripPlan {
   int cb, seg, tiles_per_row, num_segments, cblocks, cb_per_unit, cb_groups, ndy, dy_groups, co_tiles, splits, segs_per_split;
 };
@@ -501,6 +742,47 @@ static WgradStripPlan wgrad_strip_plan(const FpConvDesc* d) {
   w.segs_per_split = (w.num_segments + want - 1) / want;
   w.splits = (w.num_segments + w.segs_per_split - 1) / w.segs_per_split;
   return w;
+}
+
+struct WgradRollPlan { int cb, seg, tiles_per_row, num_cols, cblocks, cb_per_unit, cb_groups, splits, cols_per_split; };
+
+// rolling variant: opt-in (FP_WGRAD_ROLL=1), strip-eligible layers with Cout <= 64
+static bool wgrad_roll_ok(const FpConvDesc* d) {
+  const char* renv = getenv("FP_WGRAD_ROLL");
+  return renv && atoi(renv) == 1 && d->cout <= 64 && wgrad_strip_ok(d);
+}
+
+static WgradRollPlan wgrad_roll_plan(const FpConvDesc* d) {
+  WgradRollPlan w;
+  w.cb = wgrad_strip_cb(d);
+  w.seg = wgrad_strip_seg(d->wo, 64);                          // always the longest segments: one TMA box per dZ row
+  w.tiles_per_row = (d->wo + w.seg - 1) / w.seg;
+  w.num_cols = d->batch * w.tiles_per_row;
+  w.cblocks = (d->c0 + d->c1) / w.cb;
+  const int max_cb = 256 / (3 * w.cb);                         // pair block and single block: 256 TMEM columns each
+  w.cb_groups = (w.cblocks + max_cb - 1) / max_cb;
+  w.cb_per_unit = (w.cblocks + w.cb_groups - 1) / w.cb_groups;
+  w.cb_groups = (w.cblocks + w.cb_per_unit - 1) / w.cb_per_unit;
+  int want = num_sms() / w.cb_groups;
+  if (want < 1) want = 1;
+  if (want > w.num_cols) want = w.num_cols;
+  w.cols_per_split = (w.num_cols + want - 1) / want;
+  w.splits = (w.num_cols + w.cols_per_split - 1) / w.cols_per_split;
+  return w;
+}
+
+template <int CB>
+static int launch_wgrad_roll(const WgradRollParams& rp, const CUtensorMap& tm, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_roll_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         wr_smem_bytes<CB>());
+    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(wgrad roll): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  conv_wgrad_roll_kernel<CB><<<grid, WG_THREADS, wr_smem_bytes<CB>(), st>>>(rp, tm);
+  FP_CHECK_LAUNCH("fp_conv_wgrad(roll)");
+  return FP_OK;
 }
 
 template <int CB>
@@ -582,6 +864,10 @@ using namespace fp;
 
 extern "C" long long fp_conv_wgrad_workspace_bytes(const FpConvDesc* d) {
   if (d == nullptr) return -1;
+  if (wgrad_roll_ok(d)) {
+    const WgradRollPlan wr = wgrad_roll_plan(d);
+    return static_cast<long long>(wr.splits) * 64 * d->kpad * 4;
+  }
   if (wgrad_strip_ok(d)) {
     const WgradStripPlan ws = wgrad_strip_plan(d);
     return static_cast<long long>(ws.splits) * ws.co_tiles * 128 * d->kpad * 4;
@@ -602,6 +888,30 @@ extern "C" int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int cin_r = stem ? 3 : d->c0 + d->c1;
   const int kh_r = stem ? 7 : d->kh, kw_r = stem ? 7 : d->kw;
+  if (!stem && wgrad_roll_ok(d)) {
+    WgradRollParams rp{};
+    rp.g = p.g;
+    const WgradRollPlan wr = wgrad_roll_plan(d);
+    rp.Cout = d->cout; rp.kpad = d->kpad; rp.cin = d->c0 + d->c1;
+    rp.seg = wr.seg; rp.tiles_per_row = wr.tiles_per_row; rp.num_cols = wr.num_cols;
+    rp.cblocks = wr.cblocks; rp.cb_per_unit = wr.cb_per_unit; rp.cb_groups = wr.cb_groups;
+    rp.splits = wr.splits; rp.cols_per_split = wr.cols_per_split;
+    rp.partial = workspace; rp.a_fmt = grad_dtype; rp.b_fmt = d->dtype;
+    CUtensorMap tmap_dz4;
+    rc = make_tmap_nhwc(&tmap_dz4, dz, static_cast<uint64_t>(dz_ld), static_cast<uint64_t>(d->wo),
+                        static_cast<uint64_t>(d->ho), static_cast<uint64_t>(d->batch), 64u,
+                        static_cast<uint32_t>(wr.seg), 128);
+    if (rc != FP_OK) return rc;
+    const int grid_r = wr.cb_groups * wr.splits;
+    rc = wr.cb == 64 ? launch_wgrad_roll<64>(rp, tmap_dz4, grid_r, st)
+                     : (wr.cb == 32 ? launch_wgrad_roll<32>(rp, tmap_dz4, grid_r, st) : launch_wgrad_roll<16>(rp, tmap_dz4, grid_r, st));
+    if (rc != FP_OK) return rc;
+    const long long total_r = static_cast<long long>(d->cout) * d->kpad;
+    wgrad_reduce_kernel<<<static_cast<unsigned>((total_r + 255) / 256), 256, 0, st>>>(
+        workspace, wr.splits, 64, d->kpad, d->cout, cin_r, d->c0 + d->c1, kh_r, kw_r, 0, accumulate, dw_oihw);
+    FP_CHECK_LAUNCH("fp_conv_wgrad(roll reduce)");
+    return FP_OK;
+  }
   if (!stem && wgrad_strip_ok(d)) {
     WgradStripParams sp{};
     sp.g = p.g;

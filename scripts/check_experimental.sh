@@ -11,5 +11,7 @@ echo "== layer times, default dispatch"
 TOP=400 timeout 200 python scripts/layer_times.py 2>&1 | grep -E "step ms|^\{|fwd|dgrad" | head -24
 echo "== layer times, FP_ROWSTREAM=1"
 FP_ROWSTREAM=1 TOP=400 timeout 200 python scripts/layer_times.py 2>&1 | grep -E "step ms|^\{|fwd|dgrad" | head -24
-echo "== end-to-end parity with FP_ROWSTREAM=1"
-FP_ROWSTREAM=1 timeout 400 python -m pytest tests/test_gpu_forward.py tests/test_gpu_train.py -q -m gpu -x 2>&1 | tail -5
+echo "== layer times, FP_WGRAD_ROLL=1"
+FP_WGRAD_ROLL=1 TOP=400 timeout 200 python scripts/layer_times.py 2>&1 | grep -E "step ms|^\{|wgrad" | head -24
+echo "== end-to-end parity with FP_ROWSTREAM=1 FP_WGRAD_ROLL=1"
+FP_ROWSTREAM=1 FP_WGRAD_ROLL=1 timeout 400 python -m pytest tests/test_gpu_forward.py tests/test_gpu_train.py -q -m gpu -x 2>&1 | tail -5

@@ -5,6 +5,8 @@ GPU budget was spent and have not run on hardware yet).  Enable with FP_TEST_EXP
 
 * conv_rowstream_kernel (FP_ROWSTREAM=1): row-streaming 3x3 convolution, one N = 3*Cout tcgen05.mma per (input row,
   dx, K step); compared against the default strip kernel and against torch's conv2d on the same 16-bit operands.
+* conv_wgrad_roll_kernel (FP_WGRAD_ROLL=1): rolling, row-paired weight gradient (Cout <= 64); compared against the
+  default weight-gradient kernels and autograd.
 * the non-default dispatch variants selected by environment variables: the same convolution must
   come out of every variant.
 """
@@ -124,3 +126,56 @@ def test_dispatch_variants_agree(cfg, env):
             os.environ.pop(k, None)
     assert torch.isfinite(var).all()
     assert (var - base).abs().max().item() <= 2e-2 * base.abs().max().item()
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(c0=64, c1=0, up0=0, pad=1, pad_mode=1, cout=64, h=9, w=160, b=2),       # CB 64, one 160-pixel segment per row
+    dict(c0=32, c1=0, up0=0, pad=1, pad_mode=1, cout=32, h=7, w=320, b=2),       # CB 32
+    dict(c0=64, c1=64, up0=1, pad=1, pad_mode=1, cout=64, h=5, w=80, b=2),       # upsample + concat: 2 channel blocks -> 2 CTAs groups
+    dict(c0=32, c1=0, up0=0, pad=1, pad_mode=1, cout=2, h=6, w=200, b=3),        # a head (cout 2, dz_ld 8), ragged segments
+    dict(c0=64, c1=0, up0=0, pad=1, pad_mode=0, cout=48, h=11, w=100, b=1),      # zero padding
+])
+def test_wgrad_roll_matches_default_and_autograd(cfg):
+    lib = _lib.load()
+    _lib.require_device()
+    g = torch.Generator().manual_seed(13)
+    b, h0, w0 = cfg['b'], cfg['h'], cfg['w']
+    c0, c1, cout, pad = cfg['c0'], cfg['c1'], cfg['cout'], cfg['pad']
+    hin, win = (2 * h0, 2 * w0) if cfg['up0'] else (h0, w0)
+    cin = c0 + c1
+    x0 = torch.randn(b, c0, h0, w0, generator=g).to(DT).float().cuda()
+    x1 = torch.randn(b, c1, hin, win, generator=g).to(DT).float().cuda() if c1 else None
+    wgt = (torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5).to(DT).float().cuda().requires_grad_(True)
+    xin = F.interpolate(x0, scale_factor=2, mode='nearest') if cfg['up0'] else x0
+    if x1 is not None:
+        xin = torch.cat([xin, x1], 1)
+    if cfg['pad_mode'] == 1:
+        z = F.conv2d(F.pad(xin, (1, 1, 1, 1), mode='reflect'), wgt)
+    else:
+        z = F.conv2d(xin, wgt, padding=pad)
+    dz = torch.randn(z.shape, generator=g).to(DT).float().cuda()
+    z.backward(dz)
+    ho, wo = z.shape[2], z.shape[3]
+    ld = max(8, cout)
+    dz16 = torch.zeros(b, ho, wo, ld, dtype=DT, device='cuda')
+    dz16[..., :cout] = dz.permute(0, 2, 3, 1).to(DT)
+    d = FpConvDesc(batch=b, c0=c0, h0=h0, w0=w0, up0=cfg['up0'], c1=c1, kh=3, kw=3, stride=1, pad_t=pad, pad_l=pad,
+                   pad_mode=cfg['pad_mode'], ho=ho, wo=wo, cout=cout, kpad=(9 * cin + 63) // 64 * 64, npad=0, bn=64, act=0,
+                   dtype=BF, out_f32=0, out_ld=cout, res_ld=0, b_via_tma=1, w_dtype_plus1=0)
+    s0 = x0.permute(0, 2, 3, 1).contiguous().to(DT)
+    s1 = x1.permute(0, 2, 3, 1).contiguous().to(DT) if x1 is not None else None
+    outs = {}
+    for mode in ('0', '1'):
+        os.environ['FP_WGRAD_ROLL'] = mode
+        try:
+            nbytes = lib.fp_conv_wgrad_workspace_bytes(ctypes.byref(d))
+            wsp = torch.empty(nbytes // 4 + 1, dtype=torch.float32, device='cuda')
+            dw = torch.full((cout, cin, 3, 3), float('nan'), dtype=torch.float32, device='cuda')
+            _lib.check(lib.fp_conv_wgrad(ctypes.byref(d), P(s0), P(s1), P(dz16), ld, BF, 0, 0, P(dw), P(wsp), None))
+            torch.cuda.synchronize()
+            outs[mode] = dw
+        finally:
+            os.environ.pop('FP_WGRAD_ROLL', None)
+    tol = 2e-3 * wgt.grad.abs().max().item() + 1e-4
+    assert (outs['0'] - wgt.grad).abs().max().item() <= tol
+    assert (outs['1'] - wgt.grad).abs().max().item() <= tol
