@@ -76,3 +76,18 @@ def test_model_manager_surface(tmp_path):
     mm2.load_model(str(tmp_path / 'weights_0'))
     for a, b in zip(mm.model.state_dict().values(), mm2.model.state_dict().values()):
         assert torch.equal(a, b)
+
+
+def test_every_environment_switch_is_documented():
+    """Each FP_* variable the library reads (csrc getenv calls) is listed in INTEGRATION.md."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for f in glob.glob(os.path.join(root, 'footprints_b200', 'csrc', '*.cu')) + glob.glob(os.path.join(root, 'footprints_b200', 'csrc', '*.cuh')):
+        if os.path.basename(f) in ('test_harness.cu', 'probe_umma_shift.cu'):
+            continue
+        names |= set(re.findall(r'getenv\("(FP_[A-Z_]+)"\)', open(f).read()))
+    doc = open(os.path.join(root, 'INTEGRATION.md')).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert names and not missing, missing
