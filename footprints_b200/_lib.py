@@ -32,6 +32,7 @@ PROTOTYPES = {
     'fp_version': (ctypes.c_int, []),
     'fp_last_error': (ctypes.c_char_p, []),
     'fp_check_device': (ctypes.c_int, []),
+    'fp_reload_options': (ctypes.c_int, []),
     'fp_conv_fwd': (ctypes.c_int, [ctypes.POINTER(FpConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'fp_pack_conv_weight': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_pack_stem_weight': (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),

@@ -2,9 +2,13 @@
 // run time so the library links against cudart only).
 #include "fp_internal.h"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cudaTypedefs.h>
+#include <mutex>
+#include <unordered_set>
 
 namespace fp {
 
@@ -18,10 +22,67 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
-static int g_num_sms = 0;
-static int g_dev_status = 1;  // 1 = unknown
+// per-device state (CUDA function attributes and properties are per device; one process may drive several GPUs)
+constexpr int kMaxDevices = 64;
+static int g_num_sms[kMaxDevices];            // 0 = unknown
+static int g_dev_status[kMaxDevices];         // 0 = unknown, 1 = ok, < 0 = error code
+static std::mutex g_mu;
+static std::unordered_set<unsigned long long> g_attr_done;
 
-int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
+}
+
+int num_sms() {
+  const int dev = current_device();
+  return (dev >= 0 && g_num_sms[dev] > 0) ? g_num_sms[dev] : 148;
+}
+
+int ensure_max_smem(const void* kernel, int bytes, const char* what) {
+  const int dev = current_device();
+  if (dev < 0) return set_error(FP_ERR_CUDA, "%s: no current CUDA device", what);
+  const unsigned long long key = (reinterpret_cast<unsigned long long>(kernel) << 6) ^ static_cast<unsigned long long>(dev);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_attr_done.count(key)) return FP_OK;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(%s, smem=%d): %s", what, bytes, cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_attr_done.insert(key);
+  return FP_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static Options g_opts;
+static std::atomic<int> g_opts_loaded{0};
+static void load_options() {
+  Options o;
+  o.strip = env_int("FP_STRIP", 1);
+  o.strip_mineff = env_int("FP_STRIP_MINEFF", 80);
+  o.strip_tma = env_int("FP_STRIP_TMA", 1);
+  o.strip_wres = env_int("FP_STRIP_WRES", 1);
+  o.rowstream = env_int("FP_ROWSTREAM", 1);
+  o.rowstream_mineff = env_int("FP_ROWSTREAM_MINEFF", 60);
+  o.a_mode = env_int("FP_A_MODE", 0);
+  o.debug_flags = env_int("FP_DEBUG_FLAGS", 0);
+  o.wgrad_strip = env_int("FP_WGRAD_STRIP", 1);
+  o.wgrad_roll = env_int("FP_WGRAD_ROLL", 1);
+  o.wgrad_fuse_taps = env_int("FP_WGRAD_FUSE_TAPS", 1);
+  o.head_tile = env_int("FP_HEAD_TILE", 1);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_opts = o;
+  g_opts_loaded.store(1);
+}
+const Options& opts() {
+  if (!g_opts_loaded.load()) load_options();
+  return g_opts;
+}
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -96,20 +157,26 @@ int make_tmap_3d_sw128(CUtensorMap* out, const void* base, uint64_t cols, uint64
 extern "C" int fp_version(void) { return FP_VERSION; }
 extern "C" const char* fp_last_error(void) { return fp::g_err; }
 
+extern "C" int fp_reload_options(void) {
+  fp::load_options();
+  return FP_OK;
+}
+
 extern "C" int fp_check_device(void) {
   using namespace fp;
-  if (g_dev_status <= 0) return g_dev_status == 0 ? FP_OK : set_error(g_dev_status, "%s", g_err);
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(e));
+  if (dev < 0 || dev >= kMaxDevices) return set_error(FP_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
+  if (g_dev_status[dev] == 1) return FP_OK;
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, dev);
   if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
-  if (prop.major != 10) {
-    g_dev_status = FP_ERR_ARCH;
-    return set_error(FP_ERR_ARCH, "device is sm_%d%d; footprints_b200 kernels are sm_100a only", prop.major, prop.minor);
+  if (prop.major != 10 || prop.minor != 0) {       // the library carries an sm_100a image only (sm_103 cannot run it)
+    g_dev_status[dev] = FP_ERR_ARCH;
+    return set_error(FP_ERR_ARCH, "device %d is sm_%d%d; footprints_b200 kernels are sm_100a only", dev, prop.major, prop.minor);
   }
-  g_num_sms = prop.multiProcessorCount;
-  g_dev_status = 0;
+  g_num_sms[dev] = prop.multiProcessorCount;
+  g_dev_status[dev] = 1;
   return FP_OK;
 }

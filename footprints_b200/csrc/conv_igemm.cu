@@ -483,13 +483,8 @@ template <int BN>
 static int launch_igemm(const IgemmParams& p, const CUtensorMap& tmap, const CUtensorMap& tmap_a0,
                         const CUtensorMap& tmap_a1, cudaStream_t stream) {
   using Cfg = IgemmCfg<BN>;
-  static bool attr_set = false;
   auto kern = conv_igemm_kernel<BN>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-    attr_set = true;
-  }
+  { const int arc = ensure_max_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, "kern"); if (arc != FP_OK) return arc; }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p, tmap, tmap_a0, tmap_a1);
   cudaError_t e = cudaGetLastError();
@@ -1103,29 +1098,17 @@ conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_c
   }
 }
 
-// minimum fraction (percent) of the 128-pixel row segments that must be real output pixels (FP_STRIP_MINEFF)
-static int strip_min_eff() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FP_STRIP_MINEFF"); v = e ? atoi(e) : 80; }
-  return v;
-}
 
 template <int BN, int CB>
 static int launch_strip(const StripParams& sp_in, const CUtensorMap& tmap, const CUtensorMap& tmap_x, cudaStream_t stream) {
   using Cfg = StripCfg<BN, CB>;
-  static bool attr_set = false;
   auto kern = conv_igemm_strip_kernel<BN, CB>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_MAX);
-    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(strip smem=%d): %s", Cfg::SMEM_MAX, cudaGetErrorString(e));
-    attr_set = true;
-  }
+  { const int arc = ensure_max_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_MAX, "kern"); if (arc != FP_OK) return arc; }
   StripParams sp = sp_in;
   // resident filter if it fits beside >= 3 strip stages (single channel tile only), else stream it per stage
-  const char* wenv = getenv("FP_STRIP_WRES");
   const int w_bytes = 9 * sp.cblocks * Cfg::B_TILE;
   const int room = Cfg::SMEM_MAX - Cfg::FIXED_BYTES - w_bytes;
-  if (sp.b.n_tiles == 1 && room >= 3 * Cfg::A_BYTES && !(wenv && atoi(wenv) == 0)) {
+  if (sp.b.n_tiles == 1 && room >= 3 * Cfg::A_BYTES && opts().strip_wres != 0) {
     sp.w_resident = 1;
     sp.w_bytes = w_bytes;
     sp.stage_bytes = Cfg::A_BYTES;
@@ -1163,13 +1146,8 @@ static int launch_rowstream(const StripParams& sp, const CUtensorMap& tmap, cons
   rp.H = SLOTS / 2;
   rp.chunks_per_col = (sp.b.g.Ho + rp.H - 1) / rp.H;
   rp.total_items = sp.b.g.M / sp.b.g.HoWo * sp.tiles_per_row * rp.chunks_per_col;
-  static bool attr_set = false;
   auto kern = conv_rowstream_kernel<BN, CB>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_MAX);
-    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(rowstream): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  { const int arc = ensure_max_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_MAX, "kern"); if (arc != FP_OK) return arc; }
   const int smem_bytes = RS_FIXED + rp.stages * Cfg::A_BYTES + rp.w_bytes;
   const int grid = rp.total_items < num_sms() ? rp.total_items : num_sms();
   kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(rp, tmap, tmap_x);
@@ -1239,7 +1217,7 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
   p.act = d->act; p.fmt = d->dtype; p.w_fmt = d->w_dtype_plus1 ? d->w_dtype_plus1 - 1 : d->dtype;
   p.out_f32 = d->out_f32; p.out_ld = d->out_ld; p.res_ld = d->res_ld;
   p.b_via_tma = d->b_via_tma;
-  { const char* e = getenv("FP_DEBUG_FLAGS"); p.debug = e ? atoi(e) : 0; }
+  p.debug = opts().debug_flags;
 
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
@@ -1252,9 +1230,8 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
   CUtensorMap tmap_a0, tmap_a1;
   memset(&tmap_a0, 0, sizeof(tmap_a0));
   memset(&tmap_a1, 0, sizeof(tmap_a1));
-  const char* amode_env = getenv("FP_A_MODE");
   const bool gather_ok = (d->c0 % 64 == 0) && (d->c1 % 64 == 0) && d->b_via_tma;
-  p.a_mode = (gather_ok && amode_env && atoi(amode_env) == 1) ? 1 : 0;   // opt-in (FP_A_MODE=1): measured no faster than cp.async
+  p.a_mode = (gather_ok && opts().a_mode == 1) ? 1 : 0;   // opt-in (FP_A_MODE=1): measured no faster than cp.async
   if (p.a_mode == 1) {
     p.rows0 = d->batch * d->h0 * d->w0;
     p.rows1 = d->batch * p.g.Hin * p.g.Win;
@@ -1268,13 +1245,17 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // row-strip kernel: 3x3 stride-1, 64-channel blocks, wide rows (>= 80 % of the 128-pixel row segments are used)
   {
-    const char* senv = getenv("FP_STRIP");
     const int segs = (d->wo + BM - 1) / BM;
     const int cb = (d->c0 % 64 == 0 && d->c1 % 64 == 0) ? 64 : ((d->c0 % 32 == 0 && d->c1 % 32 == 0) ? 32 : 0);
     const bool strip_ok = d->kh == 3 && d->kw == 3 && d->stride == 1 && d->up0 != 2 && cb != 0 && d->b_via_tma &&
                           d->bn <= 128 && d->bn >= 32 && (cb == 64 || d->bn <= 64) && d->kpad >= 9 * (d->c0 + d->c1) &&
-                          d->wo * 100 >= segs * BM * strip_min_eff() && !(senv && atoi(senv) == 0);
-    if (strip_ok) {
+                          opts().strip != 0;
+    // used fraction of the 128-pixel row segments: the strip kernel (3 fills per tile instead of 9) pays off from ~80 %;
+    // the row-streaming kernel (<= 1.5 fills per output row, N = 3*Cout instructions) already from ~60 % -- that brings
+    // the 48x160 / 24x80 layers (Wo = 160 / 80: 62.5 %) onto it
+    const int eff = d->wo * 100 / (segs * BM);
+    const bool rs_ok = strip_ok && opts().rowstream != 0 && d->bn <= 64 && d->npad == d->bn && eff >= opts().rowstream_mineff;
+    if (strip_ok && (rs_ok || eff >= opts().strip_mineff)) {
       StripParams sp{};
       sp.b = p;
       sp.tiles_per_row = segs;
@@ -1290,17 +1271,15 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
       // zero-padded single-source inputs (every data-gradient full correlation): strips straight from the copy engine
       CUtensorMap tmap_x;
       memset(&tmap_x, 0, sizeof(tmap_x));
-      const char* xenv = getenv("FP_STRIP_TMA");
-      if (d->pad_mode == FP_PAD_ZERO && d->up0 == 0 && d->c1 == 0 && !(xenv && atoi(xenv) == 0)) {
+      if (d->pad_mode == FP_PAD_ZERO && d->up0 == 0 && d->c1 == 0 && opts().strip_tma != 0) {
         rc = make_tmap_nhwc(&tmap_x, src0, static_cast<uint64_t>(d->c0), static_cast<uint64_t>(d->w0),
                             static_cast<uint64_t>(d->h0), static_cast<uint64_t>(d->batch), static_cast<uint32_t>(cb),
                             static_cast<uint32_t>(STRIP_PIX), cb * 2);
         if (rc != FP_OK) return rc;
         sp.x_via_tma = 1;
       }
-      {   // experimental row-streaming kernel (opt-in; see conv_rowstream_kernel): Cout tile <= 64, single channel tile
-        const char* renv = getenv("FP_ROWSTREAM");
-        if (renv && atoi(renv) == 1 && d->bn <= 64 && sp.b.n_tiles == 1) {
+      {   // row-streaming kernel (see conv_rowstream_kernel): Cout tile <= 64, single channel tile
+        if (rs_ok) {
           int rrc = FP_ERR_UNSUPPORTED;
           if (cb == 64 && d->bn == 32) rrc = launch_rowstream<32, 64>(sp, tmap_s, tmap_x, st);
           else if (cb == 64 && d->bn == 64) rrc = launch_rowstream<64, 64>(sp, tmap_s, tmap_x, st);
@@ -1308,6 +1287,7 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
           else if (cb == 32 && d->bn == 64) rrc = launch_rowstream<64, 32>(sp, tmap_s, tmap_x, st);
           if (rrc != FP_ERR_UNSUPPORTED) return rrc;
         }
+        if (eff < opts().strip_mineff) goto general_kernel;     // too ragged for the plain strip kernel
       }
       if (cb == 64) {
         switch (d->bn) {
@@ -1325,6 +1305,7 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
       }
     }
   }
+general_kernel:
   switch (d->bn) {
     case 16: return launch_igemm<16>(p, tmap, tmap_a0, tmap_a1, st);
     case 32: return launch_igemm<32>(p, tmap, tmap_a0, tmap_a1, st);

@@ -712,13 +712,12 @@ static int wgrad_strip_seg(int wo, int cb) {
 }
 
 static bool wgrad_strip_ok(const FpConvDesc* d) {
-  const char* senv = getenv("FP_WGRAD_STRIP");
   const int cb = wgrad_strip_cb(d);
   const int seg = wgrad_strip_seg(d->wo, cb);
   const int segs = (d->wo + seg - 1) / seg;
   const int cin = d->c0 + d->c1;
   return d->kh == 3 && d->kw == 3 && d->stride == 1 && d->up0 != 2 && cb != 0 && d->kpad >= 9 * cin &&
-         (cb == 64 || cin / cb <= 2) && d->wo >= 64 && d->wo * 100 >= segs * seg * 80 && !(senv && atoi(senv) == 0);
+         (cb == 64 || cin / cb <= 2) && d->wo >= 64 && d->wo * 100 >= segs * seg * 80 && opts().wgrad_strip != 0;
 }
 
 static WgradStripPlan wgrad_strip_plan(const FpConvDesc* d) {
@@ -746,10 +745,9 @@ static WgradStripPlan wgrad_strip_plan(const FpConvDesc* d) {
 
 struct WgradRollPlan { int cb, seg, tiles_per_row, num_cols, cblocks, cb_per_unit, cb_groups, splits, cols_per_split; };
 
-// rolling variant: opt-in (FP_WGRAD_ROLL=1), strip-eligible layers with Cout <= 64
+// rolling variant (default; FP_WGRAD_ROLL=0 falls back to the strip kernel): strip-eligible layers with Cout <= 64
 static bool wgrad_roll_ok(const FpConvDesc* d) {
-  const char* renv = getenv("FP_WGRAD_ROLL");
-  return renv && atoi(renv) == 1 && d->cout <= 64 && wgrad_strip_ok(d);
+  return opts().wgrad_roll != 0 && d->cout <= 64 && wgrad_strip_ok(d);
 }
 
 static WgradRollPlan wgrad_roll_plan(const FpConvDesc* d) {
@@ -773,13 +771,7 @@ static WgradRollPlan wgrad_roll_plan(const FpConvDesc* d) {
 
 template <int CB>
 static int launch_wgrad_roll(const WgradRollParams& rp, const CUtensorMap& tm, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_roll_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         wr_smem_bytes<CB>());
-    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(wgrad roll): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  { const int arc = ensure_max_smem(reinterpret_cast<const void*>(conv_wgrad_roll_kernel<CB>), wr_smem_bytes<CB>(), "conv_wgrad_roll_kernel"); if (arc != FP_OK) return arc; }
   conv_wgrad_roll_kernel<CB><<<grid, WG_THREADS, wr_smem_bytes<CB>(), st>>>(rp, tm);
   FP_CHECK_LAUNCH("fp_conv_wgrad(roll)");
   return FP_OK;
@@ -787,13 +779,7 @@ static int launch_wgrad_roll(const WgradRollParams& rp, const CUtensorMap& tm, i
 
 template <int CB>
 static int launch_wgrad_strip(const WgradStripParams& sp, const CUtensorMap& tm, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_strip_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ws_smem_bytes<CB>());
-    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(wgrad strip): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  { const int arc = ensure_max_smem(reinterpret_cast<const void*>(conv_wgrad_strip_kernel<CB>), ws_smem_bytes<CB>(), "conv_wgrad_strip_kernel"); if (arc != FP_OK) return arc; }
   conv_wgrad_strip_kernel<CB><<<grid, WG_THREADS, ws_smem_bytes<CB>(), st>>>(sp, tm);
   FP_CHECK_LAUNCH("fp_conv_wgrad(strip)");
   return FP_OK;
@@ -921,10 +907,7 @@ extern "C" int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* 
     sp.cb_per_unit = ws.cb_per_unit; sp.cb_groups = ws.cb_groups; sp.ndy = ws.ndy; sp.dy_groups = ws.dy_groups;
     sp.co_tiles = ws.co_tiles; sp.splits = ws.splits; sp.segs_per_split = ws.segs_per_split;
     sp.partial = workspace; sp.a_fmt = grad_dtype; sp.b_fmt = d->dtype;
-    {
-      const char* fenv = getenv("FP_WGRAD_FUSE_TAPS");
-      sp.fuse_taps = fenv ? atoi(fenv) : 1;
-    }
+    sp.fuse_taps = opts().wgrad_fuse_taps;
     CUtensorMap tmap_dz3;
     rc = make_tmap_3d_sw128(&tmap_dz3, dz, static_cast<uint64_t>(dz_ld), static_cast<uint64_t>(d->wo),
                             static_cast<uint64_t>(d->batch) * d->ho, 64u, static_cast<uint32_t>(ws.seg));
@@ -945,12 +928,7 @@ extern "C" int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* 
   p.co_tiles = w.co_tiles; p.splits = w.splits; p.blocks_per_split = w.blocks_per_split; p.num_pix_blocks = w.num_pix_blocks;
   p.partial = workspace;
   p.a_fmt = grad_dtype; p.b_fmt = d->dtype;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
-    if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  { const int arc = ensure_max_smem(reinterpret_cast<const void*>(conv_wgrad_kernel), WG_SMEM_BYTES, "conv_wgrad_kernel"); if (arc != FP_OK) return arc; }
   const int grid = p.k_groups * p.co_tiles * p.splits;
   CUtensorMap tmap_dz;
   rc = make_tmap_2d_sw128(&tmap_dz, dz, static_cast<uint64_t>(dz_ld), static_cast<uint64_t>(p.g.M), 64u, 128u);

@@ -11,7 +11,19 @@ namespace fp {
 
 // printf-style thread-local error message; returns `code` so callers can `return set_error(...)`.
 int set_error(int code, const char* fmt, ...);
-int num_sms();
+int num_sms();       // SM count of the CURRENT device (cached per device ordinal)
+
+// Tuning / triage switches.  Read from the environment ONCE (first use) instead of ~10 getenv()
+// calls per convolution launch; fp_reload_options() re-reads them (the tests flip switches inside one process).
+struct Options {
+  int strip, strip_mineff, strip_tma, strip_wres, rowstream, rowstream_mineff, a_mode, debug_flags;
+  int wgrad_strip, wgrad_roll, wgrad_fuse_taps, head_tile;
+};
+const Options& opts();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel): function attributes are per device, so
+// a process-wide `static bool` would skip the opt-in on every device but the first.
+int ensure_max_smem(const void* kernel, int bytes, const char* what);
 // 2-D row-major 16-bit matrix [rows][cols] -> tensor map with box {box_cols, box_rows}, SWIZZLE_128B.
 int make_tmap_2d_sw128(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols,
                        uint32_t box_rows);

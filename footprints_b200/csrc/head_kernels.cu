@@ -592,15 +592,9 @@ extern "C" int fp_head_conv_fwd(const void* x, const float* w_oihw, const float*
   int rc = head_check("fp_head_conv_fwd", c, h, w);
   if (rc != FP_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const char* tenv = getenv("FP_HEAD_TILE");
-  if (!(tenv && atoi(tenv) == 0)) {
+  if (opts().head_tile != 0) {
     const int tiles_x = (w + HT_COLS - 1) / HT_COLS, tiles_y = (h + HT_ROWS - 1) / HT_ROWS;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(head_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES);
-      if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(head fwd): %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
+    { const int arc = ensure_max_smem(reinterpret_cast<const void*>(head_fwd_tile_kernel), HT_SMEM_BYTES, "head_fwd_tile_kernel"); if (arc != FP_OK) return arc; }
     head_fwd_tile_kernel<<<static_cast<unsigned>(static_cast<long long>(batch) * tiles_x * tiles_y), HT_THREADS, HT_SMEM_BYTES, st>>>(
         static_cast<const uint4*>(x), w_oihw, bias, h, w, c, tiles_x, tiles_y, sigmoid, dtype, reinterpret_cast<float2*>(out));
   } else if (c <= 32) {
@@ -622,17 +616,10 @@ extern "C" int fp_head_conv_dgrad(const void* dz8, const float* w_oihw, int batc
   int rc = head_check("fp_head_conv_dgrad", c, h, w);
   if (rc != FP_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const char* tenv = getenv("FP_HEAD_TILE");
-  if (c % 16 == 0 && !(tenv && atoi(tenv) == 0)) {
+  if (c % 16 == 0 && opts().head_tile != 0) {
     const int tiles_x = (w + HT_COLS - 1) / HT_COLS, tiles_y = (h + HT_ROWS - 1) / HT_ROWS;
     const int smem = HD_SMEM_G + HD_SMEM_DZ + 9 * c * static_cast<int>(sizeof(float2));
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(head_dgrad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           HD_SMEM_G + HD_SMEM_DZ + 9 * HEAD_MAX_C * static_cast<int>(sizeof(float2)));
-      if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "cudaFuncSetAttribute(head dgrad): %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
+    { const int arc = ensure_max_smem(reinterpret_cast<const void*>(head_dgrad_tile_kernel), HD_SMEM_G + HD_SMEM_DZ + 9 * HEAD_MAX_C * static_cast<int>(sizeof(float2)), "head_dgrad_tile_kernel"); if (arc != FP_OK) return arc; }
     head_dgrad_tile_kernel<<<static_cast<unsigned>(static_cast<long long>(batch) * tiles_x * tiles_y), HT_THREADS, smem, st>>>(
         static_cast<const uint4*>(dz8), w_oihw, h, w, c, tiles_x, tiles_y, accumulate, static_cast<const uint4*>(y_act), act,
         act_dtype, grad_dtype, static_cast<uint4*>(dst));

@@ -36,6 +36,9 @@ int fp_version(void);
 const char* fp_last_error(void);
 /* 0 if the current device is sm_100 (B200); FP_ERR_ARCH / FP_ERR_CUDA otherwise. */
 int fp_check_device(void);
+/* Re-read the FP_* tuning / triage environment variables.  The library reads them once, on first
+ * use; a host that changes them afterwards (the variant-agreement tests do) calls this. */
+int fp_reload_options(void);
 
 /* Implicit-GEMM convolution on tcgen05 tensor cores: M = batch*ho*wo output pixels, N = cout,
  * K = kh*kw*(c0+c1).  The A operand is gathered on the fly from up to two NHWC sources, which

@@ -1,0 +1,14 @@
+#!/bin/bash
+# Round-2 GPU job: full GPU suite (kept log), smoke, per-layer times, bench line.  Usage: bash scripts/r02_job.sh <tag>
+set -u
+export PYTHONUNBUFFERED=1
+TAG=${1:-x}
+mkdir -p gpurun_out
+echo "== pytest -m gpu"
+timeout 1500 python -m pytest tests -m gpu -q -x -s 2>&1 | tee gpurun_out/${TAG}_pytest_gpu.log | grep -vE "^\s*$" | tail -40
+echo "== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tee gpurun_out/${TAG}_smoke.log | tail -8
+echo "== layer times"
+TOP=400 timeout 200 python scripts/layer_times.py > gpurun_out/${TAG}_layer_times.txt 2>&1; head -3 gpurun_out/${TAG}_layer_times.txt
+echo "== bench"
+timeout 400 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; cut -c1-400 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err

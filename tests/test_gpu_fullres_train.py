@@ -1,0 +1,133 @@
+"""GPU parity at the BENCHMARKED geometry (KITTI 192x640): the shapes at which fp_conv_fwd dispatches the row-streaming /
+strip kernels, the TMA-strip data gradients and the rolling / strip weight gradients -- the kernels that carry the bench
+line -- end to end through the module API, against (a) the committed fixture generated from the unmodified reference
+(oracle/gen_golden.py: train-mode outputs, the 21 losses, per-parameter gradient norms and samples, BatchNorm running
+statistics at 1x192x640) and (b) the CPU oracle at batch 4."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from footprints_b200 import FootprintNetwork, LossManager
+from footprints_b200.synthetic import synthetic_batch, synthetic_state_dict
+from oracle import footprints_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+# max-abs tolerance of the train-mode forward outputs vs the fp32 reference, per training storage type
+# eval forward (fp16 storage), same bars as tests/test_gpu_forward.py
+TOL = {'fp16': {'1/8': 4e-3, '1/4': 2e-3, '1/2': 1e-3, '1/1': 1e-3}}
+TRAIN_TOL = {'fp16': {'1/8': 4e-3, '1/4': 2e-3, '1/2': 1e-3, '1/1': 1e-3},
+             'bf16': {'1/8': 3e-2, '1/4': 2e-2, '1/2': 1e-2, '1/1': 1e-2}}
+
+
+def _net(trained_like=True):
+    net = FootprintNetwork(pretrained=False)
+    net.load_state_dict(synthetic_state_dict('resnet34', 0, trained_like=trained_like))
+    return net.cuda().train()
+
+
+def _cos(a, r):
+    a, r = a.double().flatten(), r.double().flatten()
+    return (torch.dot(a, r) / (a.norm() * r.norm() + 1e-300)).item()
+
+
+def test_train_step_fullres_matches_reference_fixture():
+    """1x192x640, ResNet-34: every quantity the fixture holds for the reference's own train step."""
+    g = np.load(os.path.join(GOLD, 'ref_resnet34_b1_192x640.npz'))
+    net = _net()
+    tol = TRAIN_TOL[net.train_dtype]
+    data = synthetic_batch(1, 192, 640, 1)
+    out = net(data['image'].cuda())
+    for k in O.SCALES:
+        idx = torch.from_numpy(g[f'train/{k}/idx']).long()
+        err = np.abs(out[k].detach().cpu().flatten()[idx].numpy() - g[f'train/{k}/val']).max()
+        print(f'train fwd 1x192x640 scale {k}: max abs err vs reference fixture {err:.3e} (bar {tol[k]:.0e})')
+        assert err <= tol[k], (k, err)
+    targets = {k: v.cuda() for k, v in data.items() if k != 'image'}
+    losses = LossManager((0.1, 100.0), 0.25, side_outputs=False)(out, targets)
+    for k, v in losses.items():
+        name = 'loss/' + (k if isinstance(k, str) else f'{k[0]}@{k[1]}')
+        ref = float(g[name])
+        assert abs(v.item() - ref) <= 5e-3 * max(1.0, abs(ref)), (name, v.item(), ref)
+    net.zero_grad()
+    losses['loss'].backward()
+    named = dict(net.named_parameters())
+    worst = 1.0
+    for name, ref_norm in zip(g['grad_names'], g['grad_norms']):
+        name = str(name)
+        grad = named[name].grad
+        assert grad is not None and torch.isfinite(grad).all(), name
+        n = grad.double().norm().item()
+        assert abs(n - ref_norm) <= 0.1 * ref_norm + 1e-12, (name, n, ref_norm)
+        idx = torch.from_numpy(g[f'grad/{name}/idx']).long()
+        ref = torch.from_numpy(g[f'grad/{name}/val'])
+        got = grad.flatten().cpu()[idx]
+        if name.startswith(('mask_decoder', 'depth_decoder')):
+            assert (got - ref).abs().max() <= 0.1 * ref.abs().max() + 1e-9, name
+            if ref.numel() >= 16:
+                worst = min(worst, _cos(got, ref))
+    print(f'worst sampled decoder gradient cosine vs reference fixture: {worst:.4f}')
+    assert worst >= 0.98
+    sd = net.state_dict()
+    for k in ('encoder.layer0.1.running_mean', 'encoder.layer0.1.running_var'):
+        assert torch.allclose(sd[k].cpu(), torch.from_numpy(g[f'bnstat/{k}']), rtol=1e-2, atol=1e-2), k
+
+
+def test_train_step_fullres_batch4_matches_oracle():
+    """4x192x640 (M tiles span images; every strip / row-streaming / rolling kernel of the bench step is dispatched):
+    outputs, loss and parameter gradients against the CPU oracle (fp32, and storage-emulating for the gradient
+    directions -- see test_gpu_train.py for why)."""
+    sd = synthetic_state_dict('resnet34', 0)
+    data = synthetic_batch(4, 192, 640, 5)
+    net = _net()
+    qd = torch.float16 if net.train_dtype == 'fp16' else torch.bfloat16
+    tol = TRAIN_TOL[net.train_dtype]
+    ref_out, ref_losses, g32, _ = O.train_step_reference(sd, data, 'resnet34')
+    _, _, gq, _ = O.train_step_reference(sd, data, 'resnet34', qdtype=qd)
+    out = net(data['image'].cuda())
+    for k in O.SCALES:
+        err = (out[k].detach().cpu() - ref_out[k].detach()).abs().max().item()
+        print(f'train fwd 4x192x640 scale {k}: max abs err vs oracle {err:.3e} (bar {tol[k]:.0e})')
+        assert err <= tol[k], (k, err)
+    targets = {k: v.cuda() for k, v in data.items() if k != 'image'}
+    losses = LossManager((0.1, 100.0), 0.25, side_outputs=False)(out, targets)
+    assert abs(losses['loss'].item() - ref_losses['loss'].item()) <= 5e-3 * ref_losses['loss'].item()
+    net.zero_grad()
+    losses['loss'].backward()
+    named = dict(net.named_parameters())
+    worst = (1.0, None)
+    for name, gref in gq.items():
+        grad = named[name].grad
+        assert grad is not None and torch.isfinite(grad).all(), name
+        a = grad.detach().float().cpu()
+        cos = _cos(a, gref)
+        floor = min(0.995, _cos(gref, g32[name])) - 0.03
+        ratio = (a.double().norm() / (gref.double().norm() + 1e-300)).item()
+        worst = min(worst, (cos, name))
+        assert cos >= floor, (name, cos, floor, ratio)
+        assert 0.9 <= ratio <= 1.1, (name, cos, ratio)
+        if name.startswith(('mask_decoder', 'depth_decoder')):
+            assert cos >= 0.99, (name, cos)
+    print(f'4x192x640: worst gradient cosine vs storage-emulating oracle {worst}')
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 96), (1, 192, 640)])
+def test_eval_forward_random_init_weights(shape):
+    """BASELINE.json config 2 is RANDOM-INIT: BatchNorm running statistics at their constructor defaults (0 / 1), the
+    worst case for absolute error because activations grow layer by layer."""
+    sd = synthetic_state_dict('resnet34', 0, trained_like=False)
+    net = FootprintNetwork(pretrained=False)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    data = synthetic_batch(*shape, 3)
+    out = net(data['image'].cuda())
+    with torch.no_grad():
+        ref = O.network_forward(sd, data['image'], 'resnet34', training=False)
+    for k in out:
+        err = (out[k].cpu() - ref[k]).abs().max().item()
+        mag = ref[k][:, :2].abs().max().item()
+        print(f'random-init eval {shape} scale {k}: max abs err {err:.3e} (logit range {mag:.2f}, bar {TOL["fp16"][k]:.0e})')
+        assert err <= TOL['fp16'][k], (k, err)

@@ -1,14 +1,11 @@
-"""Opt-in GPU tests of kernels that are compiled in but NOT dispatched by default (they were written after the round's
-GPU budget was spent and have not run on hardware yet).  Enable with FP_TEST_EXPERIMENTAL=1:
+"""GPU tests of the kernel variants behind one entry point: the same convolution / weight gradient must come out of every
+dispatch variant the FP_* switches select, and out of torch on the same 16-bit operands.
 
-    FP_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -q -m gpu
-
-* conv_rowstream_kernel (FP_ROWSTREAM=1): row-streaming 3x3 convolution, one N = 3*Cout tcgen05.mma per (input row,
-  dx, K step); compared against the default strip kernel and against torch's conv2d on the same 16-bit operands.
-* conv_wgrad_roll_kernel (FP_WGRAD_ROLL=1): rolling, row-paired weight gradient (Cout <= 64); compared against the
-  default weight-gradient kernels and autograd.
-* the non-default dispatch variants selected by environment variables: the same convolution must
-  come out of every variant.
+* conv_rowstream_kernel (default for Cout <= 64 on wide rows; FP_ROWSTREAM=0 selects the strip kernel): one N = 3*Cout
+  tcgen05.mma per (input row, dx, K step).
+* conv_wgrad_roll_kernel (default for Cout <= 64; FP_WGRAD_ROLL=0 selects the strip weight gradient).
+* FP_STRIP / FP_STRIP_TMA / FP_STRIP_WRES variants of the strip kernel.
+The library caches the switches; fp_reload_options() re-reads the environment.
 """
 import ctypes
 import os
@@ -20,9 +17,23 @@ import torch.nn.functional as F
 from footprints_b200 import _lib
 from footprints_b200._lib import FpConvDesc
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('FP_TEST_EXPERIMENTAL') != '1',
-                                 reason='experimental kernels: set FP_TEST_EXPERIMENTAL=1')]
+pytestmark = pytest.mark.gpu
+
+
+class _Env:
+    """Set FP_* switches for one block and make the library re-read them (and restore the defaults after)."""
+
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        os.environ.update(self.kv)
+        _lib.load().fp_reload_options()
+
+    def __exit__(self, *a):
+        for k in self.kv:
+            os.environ.pop(k, None)
+        _lib.load().fp_reload_options()
 BF = 1
 DT = torch.bfloat16
 
@@ -37,6 +48,9 @@ def P(t):
     dict(c0=64, c1=0, up0=1, pad=1, pad_mode=1, cout=32, h=10, w=128, b=2),     # upsampled source, BN 32 / CB 64
     dict(c0=64, c1=64, up0=1, pad=1, pad_mode=1, cout=64, h=9, w=80, b=1),      # upsample + concat, 2 channel blocks
     dict(c0=64, c1=0, up0=0, pad=2, pad_mode=0, cout=64, h=13, w=130, b=3),     # ragged last item (Ho % H != 0)
+    dict(c0=64, c1=0, up0=0, pad=1, pad_mode=0, cout=64, h=12, w=160, b=2),     # 48x160-class layer (Wo = 160: 62.5 % of 2 segments)
+    dict(c0=128, c1=0, up0=0, pad=1, pad_mode=1, cout=64, h=6, w=80, b=2),      # 24x80-class layer, 2 channel blocks
+    dict(c0=64, c1=0, up0=0, pad=2, pad_mode=0, cout=64, h=12, w=160, b=2),     # its data gradient (Wo = 162)
 ])
 def test_rowstream_matches_strip_kernel_and_torch(cfg):
     lib = _lib.load()
@@ -71,14 +85,11 @@ def test_rowstream_matches_strip_kernel_and_torch(cfg):
     ones = torch.ones(cout, device='cuda')
     outs = {}
     for mode in ('0', '1'):
-        os.environ['FP_ROWSTREAM'] = mode
-        try:
+        with _Env(FP_ROWSTREAM=mode):
             y = torch.full((b, ho, wo, cout), float('nan'), dtype=DT, device='cuda')
             _lib.check(lib.fp_conv_fwd(ctypes.byref(d), P(s0), P(s1), P(wp), P(ones), P(bias), None, P(y), None))
             torch.cuda.synchronize()
             outs[mode] = y.float().permute(0, 3, 1, 2)
-        finally:
-            os.environ.pop('FP_ROWSTREAM', None)
     tol = 2e-2 * ref.abs().max().item()
     assert (outs['0'] - ref).abs().max().item() <= tol
     assert (outs['1'] - ref).abs().max().item() <= tol
@@ -117,13 +128,14 @@ def test_dispatch_variants_agree(cfg, env):
         torch.cuda.synchronize()
         return y.float()
 
-    base = run()
-    os.environ.update(env)
-    try:
+    with _Env(FP_ROWSTREAM='0'):
+        base = run()
+    with _Env(FP_ROWSTREAM='0', **env):
         var = run()
-    finally:
-        for k in env:
-            os.environ.pop(k, None)
+    with _Env():
+        dflt = run()
+    assert torch.isfinite(dflt).all()
+    assert (dflt - base).abs().max().item() <= 2e-2 * base.abs().max().item()
     assert torch.isfinite(var).all()
     assert (var - base).abs().max().item() <= 2e-2 * base.abs().max().item()
 
@@ -166,16 +178,13 @@ def test_wgrad_roll_matches_default_and_autograd(cfg):
     s1 = x1.permute(0, 2, 3, 1).contiguous().to(DT) if x1 is not None else None
     outs = {}
     for mode in ('0', '1'):
-        os.environ['FP_WGRAD_ROLL'] = mode
-        try:
+        with _Env(FP_WGRAD_ROLL=mode):
             nbytes = lib.fp_conv_wgrad_workspace_bytes(ctypes.byref(d))
             wsp = torch.empty(nbytes // 4 + 1, dtype=torch.float32, device='cuda')
             dw = torch.full((cout, cin, 3, 3), float('nan'), dtype=torch.float32, device='cuda')
             _lib.check(lib.fp_conv_wgrad(ctypes.byref(d), P(s0), P(s1), P(dz16), ld, BF, 0, 0, P(dw), P(wsp), None))
             torch.cuda.synchronize()
             outs[mode] = dw
-        finally:
-            os.environ.pop('FP_WGRAD_ROLL', None)
     tol = 2e-3 * wgt.grad.abs().max().item() + 1e-4
     assert (outs['0'] - wgt.grad).abs().max().item() <= tol
     assert (outs['1'] - wgt.grad).abs().max().item() <= tol

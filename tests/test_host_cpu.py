@@ -87,7 +87,7 @@ def test_every_environment_switch_is_documented():
     for f in glob.glob(os.path.join(root, 'footprints_b200', 'csrc', '*.cu')) + glob.glob(os.path.join(root, 'footprints_b200', 'csrc', '*.cuh')):
         if os.path.basename(f) in ('test_harness.cu', 'probe_umma_shift.cu'):
             continue
-        names |= set(re.findall(r'getenv\("(FP_[A-Z_]+)"\)', open(f).read()))
+        names |= set(re.findall(r'(?:getenv|env_int)\("(FP_[A-Z_]+)"', open(f).read()))
     doc = open(os.path.join(root, 'INTEGRATION.md')).read()
     missing = sorted(n for n in names if n not in doc)
     assert names and not missing, missing
