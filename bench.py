@@ -37,6 +37,7 @@ def parse():
     ap.add_argument('--arch', default='resnet34', choices=['resnet34', 'resnet18'])
     ap.add_argument('--mode', default='train', choices=['train', 'infer'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying the CUDA graph of the step')
     return ap.parse_args()
 
 
@@ -179,6 +180,8 @@ def main():
         net.train()
         trainer = Trainer(net, lr=1e-4, process_group=pg)
         trainer.broadcast_parameters()
+        if not args.no_graph:
+            trainer.enable_cuda_graph()
         eng = trainer.eng
 
         def step_resident():
@@ -332,7 +335,7 @@ def main():
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'bf16' if args.mode == 'train' else 'f16', 'data': 'synthetic',
+                'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
                 'config': {'workload': ('training step: fwd (train-mode BN) + fused BCE/log-L1 loss + bwd + Adam' if args.mode == 'train'
                                         else 'inference forward') + f', {args.arch} encoder + 2 skip decoders, {H}x{W}, '
                                                                     f'batch {B}/GPU, random-init weights',

@@ -26,6 +26,15 @@ class FpConvDesc(ctypes.Structure):
         'b_via_tma', 'w_dtype_plus1')]
 
 
+class FpSplitLow(ctypes.Structure):
+    _fields_ = [('src0_lo', _vp), ('src1_lo', _vp), ('residual_lo', _vp), ('out_lo', _vp)]
+
+
+class FpPackJob(ctypes.Structure):
+    _fields_ = [('w', _vp), ('out', _vp)] + [(n, _i32) for n in (
+        'cout', 'cin', 'kh', 'kw', 'cpad', 'npad', 'kpad', 'dtype', 'flip', 'stem')] + [('first', ctypes.c_int64)]
+
+
 # name -> (restype, argtypes); every name must be exported by the library (tests check this against
 # the header as well)
 PROTOTYPES = {
@@ -34,8 +43,14 @@ PROTOTYPES = {
     'fp_check_device': (ctypes.c_int, []),
     'fp_reload_options': (ctypes.c_int, []),
     'fp_conv_fwd': (ctypes.c_int, [ctypes.POINTER(FpConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'fp_conv_fwd_split': (ctypes.c_int, [ctypes.POINTER(FpConvDesc), _vp, _vp, ctypes.POINTER(FpSplitLow), _vp, _vp, _vp, _vp, _vp, _vp]),
+    'fp_pack_conv_weight_split': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    'fp_pack_stem_weight_split': (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    'fp_stem_prep_split': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    'fp_maxpool3x3s2_split': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     'fp_pack_conv_weight': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_pack_stem_weight': (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    'fp_pack_weights_batched': (ctypes.c_int, [_vp, _i32, _i64, _vp]),
     'fp_stem_prep': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_maxpool3x3s2': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_heads_to_nchw': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
@@ -49,7 +64,7 @@ PROTOTYPES = {
     'fp_bn_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     'fp_bias_grad': (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     'fp_loss_fwd_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp, _vp]),
-    'fp_heads_bwd': (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    'fp_heads_bwd': (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     'fp_fold_bwd': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp]),
     'fp_act_bwd': (ctypes.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
     'fp_grad_add': (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
@@ -58,6 +73,7 @@ PROTOTYPES = {
     'fp_conv_wgrad': (ctypes.c_int, [ctypes.POINTER(FpConvDesc), _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     'fp_debug_read_trace': (ctypes.c_int, [_vp]),
     'fp_adam_step': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
+    'fp_adam_step_dev': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None

@@ -11,9 +11,13 @@ class NetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, image, *params):
         eng = net.train_engine()
-        outs = eng.forward_train(image)
+        # the saved activations / batch statistics live on THIS node: two forwards followed by two backwards, gradient
+        # accumulation over several forwards and train-mode forwards under no_grad all behave as with the reference
+        need = any(p.requires_grad for p in params) or image.requires_grad
+        outs, saved = eng.forward_train(image, save=need)
         ctx.net = net
         ctx.params = params
+        ctx.saved = saved
         return tuple(outs[k] for k in SCALES)
 
     @staticmethod
@@ -24,5 +28,12 @@ class NetFunction(torch.autograd.Function):
             if g is None:
                 raise RuntimeError(f"no gradient reached output '{k}'; the backward needs all four scales")
             douts[k] = g.contiguous().float()
-        grads = eng.backward(douts)
-        return (None, None) + tuple(grads.get(p) for p in ctx.params)
+        if ctx.saved is None:
+            raise RuntimeError('backward through a FootprintNetwork forward that saved nothing (no_grad) or was already '
+                               'back-propagated (retain_graph is not supported)')
+        saved, ctx.saved = ctx.saved, None
+        grads = eng.backward(douts, saved)
+        outs = [grads.get(p) for p in ctx.params]
+        if eng.grad_scale != 1.0:              # divide the (power-of-two) loss scale out: one multi-tensor launch
+            torch._foreach_mul_([g for g in outs if g is not None], 1.0 / eng.grad_scale)
+        return (None, None) + tuple(outs)

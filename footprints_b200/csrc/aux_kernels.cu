@@ -1,6 +1,7 @@
 // Bandwidth-bound helper kernels around the implicit-GEMM convolution: weight packing, the stem's
 // normalise + space-to-depth, max-pool, and the heads' bilinear upsample into the NCHW fp32 outputs.
 #include "fp_internal.h"
+#include "fp_ptx.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -12,8 +13,7 @@ __device__ __forceinline__ uint16_t to16(float v, int fmt) {
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     return *reinterpret_cast<uint16_t*>(&h);
   }
-  __half h = __float2half_rn(v);
-  return *reinterpret_cast<uint16_t*>(&h);
+  return static_cast<uint16_t>(fp::f32x2_to_f16x2_sat(v, 0.f) & 0xFFFFu);
 }
 
 // ---------------------------------------------------------------------------------- weight packing
@@ -48,6 +48,44 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, int cout, i
   float v = 0.f;
   if (n < cout && c < 3 && ky >= 0 && ky < 7 && kx >= 0 && kx < 7) v = w[((n * 3 + c) * 7 + ky) * 7 + kx];
   out[idx] = to16(v, fmt);
+}
+
+// One launch for every weight tensor of the network (training re-packs all ~142 operands each step: forward and
+// 180-degree-rotated data-gradient layouts).  `jobs` lives in device memory and is sorted by `first`.
+__global__ void pack_batched_kernel(const FpPackJob* __restrict__ jobs, int njobs, long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  int lo = 0, hi = njobs - 1;                       // last job whose first <= idx
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first <= idx) lo = mid; else hi = mid - 1;
+  }
+  const FpPackJob j = jobs[lo];
+  const long long local = idx - j.first;
+  const float* __restrict__ w = j.w;
+  uint16_t* __restrict__ out = static_cast<uint16_t*>(j.out);
+  float v = 0.f;
+  if (j.stem) {
+    const int n = static_cast<int>(local >> 8), k = static_cast<int>(local & 255);
+    const int tap = k >> 4, ch = k & 15;
+    const int bh = tap >> 2, bw = tap & 3;
+    const int sub = ch >> 2, c = ch & 3;
+    const int ky = 2 * bh + (sub >> 1) - 1, kx = 2 * bw + (sub & 1) - 1;
+    if (n < j.cout && c < 3 && ky >= 0 && ky < 7 && kx >= 0 && kx < 7) v = w[((n * 3 + c) * 7 + ky) * 7 + kx];
+  } else {
+    const int n = static_cast<int>(local / j.kpad);
+    const int k = static_cast<int>(local - static_cast<long long>(n) * j.kpad);
+    const int inner = j.flip ? j.cout : j.cin;
+    const int rows = j.flip ? j.cin : j.cout;
+    const int tap = k / j.cpad;
+    const int c = k - tap * j.cpad;
+    if (n < rows && tap < j.kh * j.kw && c < inner) {
+      const int ky = tap / j.kw, kx = tap - ky * j.kw;
+      if (!j.flip) v = w[((static_cast<long long>(n) * j.cin + c) * j.kh + ky) * j.kw + kx];
+      else v = w[((static_cast<long long>(c) * j.cin + n) * j.kh + (j.kh - 1 - ky)) * j.kw + (j.kw - 1 - kx)];
+    }
+  }
+  out[local] = to16(v, j.dtype);
 }
 
 // ---------------------------------------------------------------------------------- stem prep
@@ -116,6 +154,104 @@ __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int batch, int
   out[idx] = m;
 }
 
+// ---------------------------------------------------------------------------------- split-precision helpers
+__device__ __forceinline__ float from16(uint16_t u, int fmt) {
+  if (fmt == FP_BF16) return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
+  return __half2float(*reinterpret_cast<__half*>(&u));
+}
+// v -> (hi, lo) with hi = round16(v), lo = round16(v - hi)
+__device__ __forceinline__ void split16(float v, int fmt, uint16_t& hi, uint16_t& lo) {
+  hi = to16(v, fmt);
+  lo = to16(v - from16(hi, fmt), fmt);
+}
+
+// K index = tap*3*cin + part*cin + c  (stem: tap*48 + part*16 + ch of the space-to-depth formulation)
+__global__ void pack_conv_weight_split_kernel(const float* __restrict__ w, int cout, int cin, int kh, int kw, int npad,
+                                              int kpad, int fmt, int stem, uint16_t* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(npad) * kpad) return;
+  const int n = static_cast<int>(idx / kpad);
+  const int k = static_cast<int>(idx - static_cast<long long>(n) * kpad);
+  const int cg = stem ? 16 : cin;                 // channels per tap in the gathered tensor
+  const int tap = k / (3 * cg);
+  const int r = k - tap * 3 * cg;
+  const int part = r / cg;
+  const int c = r - part * cg;
+  float v = 0.f;
+  if (stem) {
+    const int bh = tap >> 2, bw = tap & 3;
+    const int sub = c >> 2, ci = c & 3;
+    const int ky = 2 * bh + (sub >> 1) - 1, kx = 2 * bw + (sub & 1) - 1;
+    if (n < cout && tap < 16 && ci < 3 && ky >= 0 && ky < 7 && kx >= 0 && kx < 7) v = w[((n * 3 + ci) * 7 + ky) * 7 + kx];
+  } else if (n < cout && tap < kh * kw) {
+    const int ky = tap / kw, kx = tap - ky * kw;
+    v = w[((static_cast<long long>(n) * cin + c) * kh + ky) * kw + kx];
+  }
+  uint16_t hi, lo;
+  split16(v, fmt, hi, lo);
+  out[idx] = part == 2 ? lo : hi;
+}
+
+__global__ void stem_prep_split_kernel(const float* __restrict__ img, int batch, int h, int w, int fmt,
+                                       uint4* __restrict__ out_hi, uint4* __restrict__ out_lo) {
+  const int hb = h >> 1, wb = w >> 1;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(batch) * hb * wb) return;
+  const int xb = static_cast<int>(idx % wb);
+  const int yb = static_cast<int>((idx / wb) % hb);
+  const int b = static_cast<int>(idx / (static_cast<long long>(wb) * hb));
+  uint16_t vh[16], vl[16];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const float2 t = *reinterpret_cast<const float2*>(
+          img + ((static_cast<long long>(b) * 3 + c) * h + (2 * yb + dy)) * w + 2 * xb);
+      split16((t.x - 0.45f) / 0.225f, fmt, vh[(dy * 2 + 0) * 4 + c], vl[(dy * 2 + 0) * 4 + c]);
+      split16((t.y - 0.45f) / 0.225f, fmt, vh[(dy * 2 + 1) * 4 + c], vl[(dy * 2 + 1) * 4 + c]);
+    }
+  }
+#pragma unroll
+  for (int s4 = 0; s4 < 4; ++s4) { vh[s4 * 4 + 3] = 0; vl[s4 * 4 + 3] = 0; }
+  uint4 o0, o1;
+  o0.x = vh[0] | (vh[1] << 16); o0.y = vh[2] | (vh[3] << 16); o0.z = vh[4] | (vh[5] << 16); o0.w = vh[6] | (vh[7] << 16);
+  o1.x = vh[8] | (vh[9] << 16); o1.y = vh[10] | (vh[11] << 16); o1.z = vh[12] | (vh[13] << 16); o1.w = vh[14] | (vh[15] << 16);
+  out_hi[idx * 2] = o0; out_hi[idx * 2 + 1] = o1;
+  o0.x = vl[0] | (vl[1] << 16); o0.y = vl[2] | (vl[3] << 16); o0.z = vl[4] | (vl[5] << 16); o0.w = vl[6] | (vl[7] << 16);
+  o1.x = vl[8] | (vl[9] << 16); o1.y = vl[10] | (vl[11] << 16); o1.z = vl[12] | (vl[13] << 16); o1.w = vl[14] | (vl[15] << 16);
+  out_lo[idx * 2] = o0; out_lo[idx * 2 + 1] = o1;
+}
+
+// max over hi + lo (fp32), split again (exact: the maximum is one of the inputs)
+__global__ void maxpool3x3s2_split_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo, int batch,
+                                          int h, int w, int c, int fmt, uint16_t* __restrict__ out_hi,
+                                          uint16_t* __restrict__ out_lo) {
+  const int ho = (h + 1) / 2, wo = (w + 1) / 2;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(batch) * ho * wo * c) return;
+  const int cc = static_cast<int>(idx % c);
+  long long t = idx / c;
+  const int ox = static_cast<int>(t % wo); t /= wo;
+  const int oy = static_cast<int>(t % ho);
+  const int b = static_cast<int>(t / ho);
+  float best = -3.0e38f;
+  uint16_t bh = 0, bl = 0;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int iy = 2 * oy + dy;
+    if (iy < 0 || iy >= h) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int ix = 2 * ox + dx;
+      if (ix < 0 || ix >= w) continue;
+      const long long o = ((static_cast<long long>(b) * h + iy) * w + ix) * c + cc;
+      const uint16_t a = in_hi[o], l = in_lo[o];
+      const float v = from16(a, fmt) + from16(l, fmt);
+      if (v > best) { best = v; bh = a; bl = l; }
+    }
+  }
+  out_hi[idx] = bh;
+  out_lo[idx] = bl;
+}
+
 // ---------------------------------------------------------------------------------- heads -> NCHW
 // torch upsample_bilinear2d, align_corners=False: src = max((dst+0.5)/scale - 0.5, 0)
 __global__ void heads_to_nchw_kernel(const float2* __restrict__ mask_head, const float2* __restrict__ depth_head,
@@ -181,6 +317,13 @@ extern "C" int fp_pack_stem_weight(const float* w, int cout, int npad, int dtype
   return FP_OK;
 }
 
+extern "C" int fp_pack_weights_batched(const FpPackJob* jobs_dev, int njobs, long long total, void* stream) {
+  if (!jobs_dev || njobs < 1 || total < 1) return set_error(FP_ERR_ARG, "fp_pack_weights_batched: bad argument");
+  pack_batched_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_dev, njobs, total);
+  FP_CHECK_LAUNCH("fp_pack_weights_batched");
+  return FP_OK;
+}
+
 extern "C" int fp_stem_prep(const float* img, int batch, int h, int w, int dtype, void* out, void* stream) {
   if (!img || !out || (h & 1) || (w & 1)) return set_error(FP_ERR_ARG, "fp_stem_prep: bad argument (h, w must be even)");
   const long long n = static_cast<long long>(batch) * (h / 2) * (w / 2);
@@ -199,6 +342,46 @@ extern "C" int fp_maxpool3x3s2(const void* in, int batch, int h, int w, int c, i
   else
     maxpool3x3s2_kernel<__half2><<<blocks_for(n, 256), 256, 0, st>>>(static_cast<const uint4*>(in), batch, h, w, c / 8, static_cast<uint4*>(out));
   FP_CHECK_LAUNCH("fp_maxpool3x3s2");
+  return FP_OK;
+}
+
+extern "C" int fp_pack_conv_weight_split(const float* w, int cout, int cin, int kh, int kw, int npad, int kpad, int dtype,
+                                         void* out, void* stream) {
+  if (!w || !out || npad < cout || kpad < 3 * kh * kw * cin) return set_error(FP_ERR_ARG, "fp_pack_conv_weight_split: bad argument");
+  const long long n = static_cast<long long>(npad) * kpad;
+  pack_conv_weight_split_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, cout, cin, kh, kw, npad, kpad, dtype, 0, static_cast<uint16_t*>(out));
+  FP_CHECK_LAUNCH("fp_pack_conv_weight_split");
+  return FP_OK;
+}
+
+extern "C" int fp_pack_stem_weight_split(const float* w, int cout, int npad, int dtype, void* out, void* stream) {
+  if (!w || !out || npad < cout) return set_error(FP_ERR_ARG, "fp_pack_stem_weight_split: bad argument");
+  const long long n = static_cast<long long>(npad) * 768;
+  pack_conv_weight_split_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, cout, 3, 7, 7, npad, 768, dtype, 1, static_cast<uint16_t*>(out));
+  FP_CHECK_LAUNCH("fp_pack_stem_weight_split");
+  return FP_OK;
+}
+
+extern "C" int fp_stem_prep_split(const float* img, int batch, int h, int w, int dtype, void* out_hi, void* out_lo,
+                                  void* stream) {
+  if (!img || !out_hi || !out_lo || (h & 1) || (w & 1)) return set_error(FP_ERR_ARG, "fp_stem_prep_split: bad argument");
+  const long long n = static_cast<long long>(batch) * (h / 2) * (w / 2);
+  stem_prep_split_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, batch, h, w, dtype, static_cast<uint4*>(out_hi), static_cast<uint4*>(out_lo));
+  FP_CHECK_LAUNCH("fp_stem_prep_split");
+  return FP_OK;
+}
+
+extern "C" int fp_maxpool3x3s2_split(const void* in_hi, const void* in_lo, int batch, int h, int w, int c, int dtype,
+                                     void* out_hi, void* out_lo, void* stream) {
+  if (!in_hi || !in_lo || !out_hi || !out_lo) return set_error(FP_ERR_ARG, "fp_maxpool3x3s2_split: null argument");
+  const long long n = static_cast<long long>(batch) * ((h + 1) / 2) * ((w + 1) / 2) * c;
+  maxpool3x3s2_split_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(in_hi), static_cast<const uint16_t*>(in_lo), batch, h, w, c, dtype,
+      static_cast<uint16_t*>(out_hi), static_cast<uint16_t*>(out_lo));
+  FP_CHECK_LAUNCH("fp_maxpool3x3s2_split");
   return FP_OK;
 }
 

@@ -44,7 +44,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int NUM_THREADS = (EPI_FIRST_WARP + NUM_EPI_WARPS) * 32;   // 544
 constexpr int ROWS_PER_THREAD = BM / (NUM_PRODUCER_THREADS / 8);     // 4
-constexpr int KTAB_ENTRIES = 1024;   // one entry per 16-byte K chunk: kpad <= 8192
+constexpr int KTAB_ENTRIES = 2048;   // one entry per 16-byte K chunk: kpad <= 16384 (split precision triples K)
 
 // perf triage hooks (FP_DEBUG_FLAGS: 1 skip A gather, 2 skip MMA, 4 skip epilogue math, 8 skip B load, 16 record
 // clock64() stamps of CTA 0 into g_trace[role][event]) are compiled in only with -DFP_TRIAGE (make TRIAGE=1):
@@ -71,7 +71,9 @@ struct IgemmParams {
   const float* scale;
   const float* shift;
   const uint8_t* residual;
+  const uint8_t* residual_lo;   // split precision: low half of the residual
   void* out;
+  void* out_lo;                 // split precision: low half of the output (y = hi + lo, both 16-bit)
   int N;
   int num_kb, kpad, m_tiles, n_tiles, total_tiles;
   int act, fmt, w_fmt, out_f32, out_ld, res_ld, b_via_tma;
@@ -103,8 +105,7 @@ __device__ __forceinline__ uint32_t pack2t(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
-  __half2 v = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+  return fp::f32x2_to_f16x2_sat(a, b);
 }
 template <int FMT>
 __device__ __forceinline__ float2 unpack2t(uint32_t u) {
@@ -117,8 +118,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
-  __half2 v = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+  return fp::f32x2_to_f16x2_sat(a, b);
 }
 __device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
   if (fmt == FP_BF16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
@@ -132,6 +132,13 @@ __device__ __forceinline__ void epilogue_store16(const IgemmParams& p, const uin
   constexpr int CW = 16;
   const int n0 = n_base + j;
   if (n0 >= p.N) return;
+  if (p.out_f32 && p.N - n0 == 2 && p.out_ld == 2 && p.residual == nullptr) {
+    // the 2-channel heads (N padded to 16): touch only the two real columns, one 8-byte store per pixel
+    const float a = apply_act<ACT>(__uint_as_float(v[0]) * s_scale[j] + s_shift[j]);
+    const float b = apply_act<ACT>(__uint_as_float(v[1]) * s_scale[j + 1] + s_shift[j + 1]);
+    *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * 2 + n0) = make_float2(a, b);
+    return;
+  }
   float f[CW];
 #pragma unroll
   for (int x = 0; x < CW; ++x) f[x] = __uint_as_float(v[x]) * s_scale[j + x] + s_shift[j + x];
@@ -153,6 +160,12 @@ __device__ __forceinline__ void epilogue_store16(const IgemmParams& p, const uin
       for (int x = 0; x < CW; ++x)
         if (x < ncols) f[x] += unpack2t<FMT>(*reinterpret_cast<const uint16_t*>(rp + x * 2)).x;
     }
+    if (p.residual_lo != nullptr) {
+      const uint8_t* rl = p.residual_lo + (static_cast<size_t>(m) * p.res_ld + n0) * 2;
+#pragma unroll
+      for (int x = 0; x < CW; ++x)
+        if (x < ncols) f[x] += unpack2t<FMT>(*reinterpret_cast<const uint16_t*>(rl + x * 2)).x;
+    }
   }
 #pragma unroll
   for (int x = 0; x < CW; ++x) f[x] = apply_act<ACT>(f[x]);
@@ -168,7 +181,35 @@ __device__ __forceinline__ void epilogue_store16(const IgemmParams& p, const uin
     }
   } else {
     uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + (static_cast<size_t>(m) * p.out_ld + n0) * 2;
-    if (ncols == CW && (p.out_ld & 7) == 0) {
+    if (p.out_lo != nullptr) {       // split precision: lo = y - hi, rounded once more (the difference is exact in fp32)
+      uint8_t* ol = reinterpret_cast<uint8_t*>(p.out_lo) + (static_cast<size_t>(m) * p.out_ld + n0) * 2;
+      float l[CW];
+#pragma unroll
+      for (int x = 0; x < CW; x += 2) {
+        const float2 hf = unpack2t<FMT>(pack2t<FMT>(f[x], f[x + 1]));
+        l[x] = f[x] - hf.x;
+        l[x + 1] = f[x + 1] - hf.y;
+      }
+      if (ncols == CW && (p.out_ld & 7) == 0) {
+#pragma unroll
+        for (int x = 0; x < CW / 8; ++x) {
+          uint4 o, q;
+          o.x = pack2t<FMT>(f[8 * x], f[8 * x + 1]); o.y = pack2t<FMT>(f[8 * x + 2], f[8 * x + 3]);
+          o.z = pack2t<FMT>(f[8 * x + 4], f[8 * x + 5]); o.w = pack2t<FMT>(f[8 * x + 6], f[8 * x + 7]);
+          q.x = pack2t<FMT>(l[8 * x], l[8 * x + 1]); q.y = pack2t<FMT>(l[8 * x + 2], l[8 * x + 3]);
+          q.z = pack2t<FMT>(l[8 * x + 4], l[8 * x + 5]); q.w = pack2t<FMT>(l[8 * x + 6], l[8 * x + 7]);
+          *reinterpret_cast<uint4*>(op + 16 * x) = o;
+          *reinterpret_cast<uint4*>(ol + 16 * x) = q;
+        }
+      } else {
+#pragma unroll
+        for (int x = 0; x < CW; ++x)
+          if (x < ncols) {
+            *reinterpret_cast<uint16_t*>(op + 2 * x) = static_cast<uint16_t>(pack2t<FMT>(f[x], 0.f) & 0xFFFF);
+            *reinterpret_cast<uint16_t*>(ol + 2 * x) = static_cast<uint16_t>(pack2t<FMT>(l[x], 0.f) & 0xFFFF);
+          }
+      }
+    } else if (ncols == CW && (p.out_ld & 7) == 0) {
 #pragma unroll
       for (int x = 0; x < CW / 8; ++x) {
         uint4 o;
@@ -360,8 +401,8 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
         KDecode kd;
         kd.second = (ke & (1u << 10)) != 0u;
         kd.padmask = (ke >> 8) & 8u;
-        kd.shy = ke & 31u; kd.shx = (ke >> 5) & 31u; kd.cc = ke >> 12;
-        kd.sbase = kd.second ? sbase1 : sbase0;
+        kd.shy = ke & 31u; kd.shx = (ke >> 5) & 31u; kd.cc = (ke >> 12) & 0x7FFFFu;
+        kd.sbase = (ke >> 31) ? (kd.second ? p.g.src1_lo : p.g.src0_lo) : (kd.second ? sbase1 : sbase0);
         kd.pstride = kd.second ? pstride1 : pstride0;
         kd.rstride = kd.second ? rstride1 : rstride0;
         const uint32_t dst = a_dst0 + s * A_STAGE_BYTES;
@@ -1048,8 +1089,9 @@ conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_c
     const int hf = (warp - EPI_FIRST_WARP) >> 2;
     const int row = q * 32 + lane;
     const int e = tid - EPI_FIRST_WARP * 32;
-    constexpr int COLS_PER_HALF = BN / 2;
-    const int col_begin = hf * COLS_PER_HALF;
+    constexpr int COLS_PER_HALF = (BN >= 32) ? BN / 2 : BN;      // BN = 16 (the 2-channel heads): one 16-column drain
+    const int col_begin = (BN >= 32) ? hf * COLS_PER_HALF : 0;
+    const bool active = (BN >= 32) || (hf == 0);
     for (int j = e; j < BN; j += NUM_EPI_THREADS) {
       s_scale[j] = (p.scale != nullptr && j < p.N) ? p.scale[j] : 1.f;
       s_shift[j] = (p.shift != nullptr && j < p.N) ? p.shift[j] : 0.f;
@@ -1070,7 +1112,11 @@ conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_c
         const bool m_ok = (x0 + row) < g.Wo && y < g.Ho;
         const uint32_t tbase = tmem_base + slot * BN + (static_cast<uint32_t>(q * 32) << 16);
 #define FP_EPI(A, F) epilogue_cols<A, F, COLS_PER_HALF>(p, tbase, col_begin, 0, m, m_ok, s_scale, s_shift, &row_empty[slot], lane)
-        if (p.fmt == FP_BF16) {
+        if (!active) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&row_empty[slot]);
+        } else if (p.fmt == FP_BF16) {
           switch (p.act) {
             case FP_ACT_RELU: FP_EPI(FP_ACT_RELU, FP_BF16); break;
             case FP_ACT_ELU: FP_EPI(FP_ACT_ELU, FP_BF16); break;
@@ -1195,13 +1241,26 @@ int fp::fill_gather_geom(const FpConvDesc* d, const void* src0, const void* src1
   return FP_OK;
 }
 
-extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* src1, const void* w_packed,
-                           const float* scale, const float* shift, const void* residual, void* out, void* stream) {
+// split == nullptr: plain 16-bit operands.  Otherwise the low halves of the sources / residual / output (fp_conv_fwd_split).
+static int conv_fwd_impl(const FpConvDesc* d, const void* src0, const void* src1, const void* w_packed,
+                         const float* scale, const float* shift, const void* residual, void* out, void* stream,
+                         const FpSplitLow* split) {
   if (d == nullptr || src0 == nullptr || w_packed == nullptr || out == nullptr)
     return set_error(FP_ERR_ARG, "fp_conv_fwd: null argument");
   IgemmParams p{};
-  int rc = fill_gather_geom(d, src0, src1, "fp_conv_fwd", p.g);
+  int rc = fill_gather_geom(d, src0, src1, "fp_conv_fwd", p.g, split == nullptr);
   if (rc != FP_OK) return rc;
+  if (split != nullptr) {
+    if (split->src0_lo == nullptr || (d->c1 > 0 && split->src1_lo == nullptr) || (residual != nullptr && split->residual_lo == nullptr))
+      return set_error(FP_ERR_ARG, "fp_conv_fwd_split: a low half is missing");
+    if (d->kpad < 3 * d->kh * d->kw * (d->c0 + d->c1)) return set_error(FP_ERR_ARG, "fp_conv_fwd_split: kpad %d < 3*taps*cin", d->kpad);
+    if (d->up0 == 2 || d->out_f32 && split->out_lo != nullptr) return set_error(FP_ERR_ARG, "fp_conv_fwd_split: unsupported mode");
+    p.g.split = 1;
+    p.g.src0_lo = static_cast<const uint8_t*>(split->src0_lo);
+    p.g.src1_lo = static_cast<const uint8_t*>(split->src1_lo);
+    p.residual_lo = static_cast<const uint8_t*>(split->residual_lo);
+    p.out_lo = split->out_lo;
+  }
   if (d->kpad > 8 * KTAB_ENTRIES) return set_error(FP_ERR_UNSUPPORTED, "fp_conv_fwd: kpad %d too large", d->kpad);
   if (d->npad % d->bn || d->npad < d->cout) return set_error(FP_ERR_ARG, "fp_conv_fwd: bad npad %d (bn %d, cout %d)", d->npad, d->bn, d->cout);
   rc = fp_check_device();
@@ -1230,7 +1289,7 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
   CUtensorMap tmap_a0, tmap_a1;
   memset(&tmap_a0, 0, sizeof(tmap_a0));
   memset(&tmap_a1, 0, sizeof(tmap_a1));
-  const bool gather_ok = (d->c0 % 64 == 0) && (d->c1 % 64 == 0) && d->b_via_tma;
+  const bool gather_ok = (d->c0 % 64 == 0) && (d->c1 % 64 == 0) && d->b_via_tma && split == nullptr;
   p.a_mode = (gather_ok && opts().a_mode == 1) ? 1 : 0;   // opt-in (FP_A_MODE=1): measured no faster than cp.async
   if (p.a_mode == 1) {
     p.rows0 = d->batch * d->h0 * d->w0;
@@ -1244,18 +1303,18 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // row-strip kernel: 3x3 stride-1, 64-channel blocks, wide rows (>= 80 % of the 128-pixel row segments are used)
-  {
+  if (split == nullptr) {
     const int segs = (d->wo + BM - 1) / BM;
     const int cb = (d->c0 % 64 == 0 && d->c1 % 64 == 0) ? 64 : ((d->c0 % 32 == 0 && d->c1 % 32 == 0) ? 32 : 0);
     const bool strip_ok = d->kh == 3 && d->kw == 3 && d->stride == 1 && d->up0 != 2 && cb != 0 && d->b_via_tma &&
-                          d->bn <= 128 && d->bn >= 32 && (cb == 64 || d->bn <= 64) && d->kpad >= 9 * (d->c0 + d->c1) &&
+                          d->bn <= 128 && d->bn >= 16 && (cb == 64 || d->bn <= 64) && d->kpad >= 9 * (d->c0 + d->c1) &&
                           opts().strip != 0;
     // used fraction of the 128-pixel row segments: the strip kernel (3 fills per tile instead of 9) pays off from ~80 %;
     // the row-streaming kernel (<= 1.5 fills per output row, N = 3*Cout instructions) already from ~60 % -- that brings
     // the 48x160 / 24x80 layers (Wo = 160 / 80: 62.5 %) onto it
     const int eff = d->wo * 100 / (segs * BM);
     const bool rs_ok = strip_ok && opts().rowstream != 0 && d->bn <= 64 && d->npad == d->bn && eff >= opts().rowstream_mineff;
-    if (strip_ok && (rs_ok || eff >= opts().strip_mineff)) {
+    if (strip_ok && (rs_ok || (eff >= opts().strip_mineff && d->bn >= 32))) {      // bn = 16: row-streaming kernel only
       StripParams sp{};
       sp.b = p;
       sp.tiles_per_row = segs;
@@ -1281,13 +1340,15 @@ extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* sr
       {   // row-streaming kernel (see conv_rowstream_kernel): Cout tile <= 64, single channel tile
         if (rs_ok) {
           int rrc = FP_ERR_UNSUPPORTED;
-          if (cb == 64 && d->bn == 32) rrc = launch_rowstream<32, 64>(sp, tmap_s, tmap_x, st);
+          if (cb == 64 && d->bn == 16) rrc = launch_rowstream<16, 64>(sp, tmap_s, tmap_x, st);
+          else if (cb == 32 && d->bn == 16) rrc = launch_rowstream<16, 32>(sp, tmap_s, tmap_x, st);
+          else if (cb == 64 && d->bn == 32) rrc = launch_rowstream<32, 64>(sp, tmap_s, tmap_x, st);
           else if (cb == 64 && d->bn == 64) rrc = launch_rowstream<64, 64>(sp, tmap_s, tmap_x, st);
           else if (cb == 32 && d->bn == 32) rrc = launch_rowstream<32, 32>(sp, tmap_s, tmap_x, st);
           else if (cb == 32 && d->bn == 64) rrc = launch_rowstream<64, 32>(sp, tmap_s, tmap_x, st);
           if (rrc != FP_ERR_UNSUPPORTED) return rrc;
         }
-        if (eff < opts().strip_mineff) goto general_kernel;     // too ragged for the plain strip kernel
+        if (eff < opts().strip_mineff || d->bn < 32) goto general_kernel;     // too ragged / too narrow for the plain strip kernel
       }
       if (cb == 64) {
         switch (d->bn) {
@@ -1314,6 +1375,18 @@ general_kernel:
     case 256: return launch_igemm<256>(p, tmap, tmap_a0, tmap_a1, st);
     default: return set_error(FP_ERR_ARG, "fp_conv_fwd: bn=%d not in {16,32,64,128,256}", d->bn);
   }
+}
+
+extern "C" int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* src1, const void* w_packed,
+                           const float* scale, const float* shift, const void* residual, void* out, void* stream) {
+  return conv_fwd_impl(d, src0, src1, w_packed, scale, shift, residual, out, stream, nullptr);
+}
+
+extern "C" int fp_conv_fwd_split(const FpConvDesc* d, const void* src0_hi, const void* src1_hi, const FpSplitLow* low,
+                                 const void* w_packed3, const float* scale, const float* shift, const void* residual_hi,
+                                 void* out_hi, void* stream) {
+  if (low == nullptr) return set_error(FP_ERR_ARG, "fp_conv_fwd_split: null argument");
+  return conv_fwd_impl(d, src0_hi, src1_hi, w_packed3, scale, shift, residual_hi, out_hi, stream, low);
 }
 
 // perf triage helper: copies CTA 0's clock stamps (FP_DEBUG_FLAGS & 16) to the host; out[3][2048]

@@ -246,6 +246,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, int a_fmt, i
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// {a, b} -> packed f16x2 (a in the low half), round-to-nearest, SATURATING: values beyond +-65504 become +-65504
+// instead of inf.  fp16 is the training storage type (activations and loss-scaled gradients); an overflow then acts as
+// an element-wise clip instead of poisoning every later layer with inf - inf = NaN.
+__device__ __forceinline__ uint32_t f32x2_to_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -6,6 +6,7 @@
 // gradient of the heads runs on the tensor-core row-strip kernel (conv_wgrad.cu); head_wgrad_kernel is the CUDA-core
 // reference implementation the tests pin it against.
 #include "fp_internal.h"
+#include "fp_ptx.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -21,8 +22,7 @@ __device__ __forceinline__ uint32_t h_pk2(float a, float b, int fmt) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
-  __half2 v = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+  return fp::f32x2_to_f16x2_sat(a, b);
 }
 __device__ __forceinline__ void h_unpack8(const uint4& v, int fmt, float (&f)[8]) {
   float2 t;

@@ -20,6 +20,11 @@ struct GatherGeom {
   int Hin, Win;              // virtual input size (after upsample) == source 1 size
   int cin_log2, taps, KH, KW, stride, pad_t, pad_l, pad_mode;
   int Ho, Wo, HoWo, M;
+  // split-precision gather (fp_conv_fwd_split): every source is a pair of 16-bit tensors hi + lo (~22 significant bits)
+  // and the K axis per tap is [hi(src0,src1) | lo(src0,src1) | hi(src0,src1)] against weights [Whi | Whi | Wlo]
+  const uint8_t* src0_lo;
+  const uint8_t* src1_lo;
+  int split;
 };
 
 __device__ __forceinline__ void make_row_info(int n, int y0, int x0, int Hv, int Wv, int up, int Hs, int Ws, int Cs,
@@ -68,16 +73,28 @@ __device__ __forceinline__ uint4 make_row_info_for_pixel(const GatherGeom& g, in
 // K-chunk table entry: chunk j covers channels [8j, 8j+8) of the tap-major K axis.
 //   [0,5) row-code shift (4*th)   [5,10) col-code shift (16+4*tw)   bit 10 source 1   bit 11 chunk is K padding
 //   [12,32) channel offset inside the source pixel
+//   bit 31: the chunk reads the LOW halves of the split-precision sources
 __device__ __forceinline__ uint32_t make_ktab_entry(const GatherGeom& g, int j, int num_chunks) {
   const int ch0 = j * 8;
-  const int tap = ch0 >> g.cin_log2;
+  int tap, cc;
+  uint32_t lo = 0u;
+  if (g.split) {
+    const int cin = g.C0 + g.C1;
+    tap = ch0 / (3 * cin);
+    const int r = ch0 - tap * 3 * cin;
+    const int part = r / cin;                   // 0: hi x Whi, 1: lo x Whi, 2: hi x Wlo
+    cc = r - part * cin;
+    lo = part == 1 ? 1u : 0u;
+  } else {
+    tap = ch0 >> g.cin_log2;
+    cc = ch0 & ((g.C0 + g.C1) - 1);
+  }
   if (j >= num_chunks || tap >= g.taps) return 1u << 11;
-  int cc = ch0 & ((g.C0 + g.C1) - 1);
   const int th = tap / g.KW, tw = tap - th * g.KW;
   const uint32_t second = cc >= g.C0 ? 1u : 0u;
   if (second) cc -= g.C0;
   return static_cast<uint32_t>(4 * th) | (static_cast<uint32_t>(16 + 4 * tw) << 5) | (second << 10) |
-         (static_cast<uint32_t>(cc) << 12);
+         (static_cast<uint32_t>(cc) << 12) | (lo << 31);
 }
 
 struct KDecode {
@@ -90,8 +107,8 @@ __device__ __forceinline__ KDecode decode_ktab(const GatherGeom& g, uint32_t ke)
   KDecode k;
   k.second = (ke & (1u << 10)) != 0u;
   k.padmask = (ke >> 8) & 8u;                                   // bit 11 -> 8: forces "invalid"
-  k.shy = ke & 31u; k.shx = (ke >> 5) & 31u; k.cc = ke >> 12;
-  k.sbase = k.second ? g.src1 : g.src0;
+  k.shy = ke & 31u; k.shx = (ke >> 5) & 31u; k.cc = (ke >> 12) & 0x7FFFFu;
+  k.sbase = (ke >> 31) ? (k.second ? g.src1_lo : g.src0_lo) : (k.second ? g.src1 : g.src0);
   k.pstride = k.second ? g.C1 : g.C0;                           // elements per source pixel
   k.rstride = k.second ? g.Win * g.C1 : g.W0 * g.C0;            // elements per source row
   return k;

@@ -4,6 +4,7 @@
 // bias gradients and Adam.  All reductions are two-stage and deterministic (no floating-point atomics),
 // mirroring the reference's cudnn.deterministic=True (footprints/training/train.py:36).
 #include "fp_internal.h"
+#include "fp_ptx.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -19,8 +20,7 @@ __device__ __forceinline__ uint32_t pk2(float a, float b, int fmt) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
-  __half2 v = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
+  return fp::f32x2_to_f16x2_sat(a, b);
 }
 __device__ __forceinline__ void unpack8(const uint4& v, int fmt, float (&f)[8]) {
   float2 t;
@@ -335,7 +335,7 @@ __global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblk
 // ------------------------------------------------------------------------------------------------
 __global__ void heads_bwd_kernel(const float* __restrict__ dout /*[B][4][H][W]*/, int ch0,
                                  const float2* __restrict__ head_post /*[B][h][w][2] or null*/, int batch, int h, int w,
-                                 int scale, int grad_fmt, uint4* __restrict__ dz) {
+                                 int scale, int grad_fmt, float gscale, uint4* __restrict__ dz) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(batch) * h * w) return;
   const int j = static_cast<int>(idx % w);
@@ -375,7 +375,7 @@ __global__ void heads_bwd_kernel(const float* __restrict__ dout /*[B][4][H][W]*/
     a1 *= s.y * (1.f - s.y);
   }
   uint4 o;
-  o.x = pk2(a0, a1, grad_fmt);
+  o.x = pk2(a0 * gscale, a1 * gscale, grad_fmt);      // loss scale: keeps fp16 inter-layer gradients in range
   o.y = o.z = o.w = 0u;
   dz[idx] = o;
 }
@@ -567,6 +567,23 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[idx] -= (lr / bc1) * (mi / denom);
 }
 
+// same update with the per-step scalars read from device memory {lr, beta1, beta2, eps, bc1, sqrt(bc2), grad_scale}: a
+// CUDA graph of the training step bakes kernel arguments in, these seven floats are refreshed by the host before each
+// replay (StepLR changes lr, the bias corrections change every step)
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long long n, const float* __restrict__ hyper) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  const float lr = hyper[0], beta1 = hyper[1], beta2 = hyper[2], eps = hyper[3], bc1 = hyper[4], bc2_sqrt = hyper[5];
+  const float gi = g[idx] * hyper[6];
+  const float mi = beta1 * m[idx] + (1.f - beta1) * gi;
+  const float vi = beta2 * v[idx] + (1.f - beta2) * gi * gi;
+  m[idx] = mi;
+  v[idx] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[idx] -= (lr / bc1) * (mi / denom);
+}
+
 static inline unsigned nblocks(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 static inline int red_blocks(long long M, int C, int blocks_per_sm = 4) {
   const int rows_per_pass = RED_THREADS / (C / 8);
@@ -681,11 +698,11 @@ extern "C" int fp_loss_fwd_bwd(const float* const* pred, float* const* grad, con
 }
 
 extern "C" int fp_heads_bwd(const float* dout_nchw, int ch0, const float* head_post, int batch, int h, int w, int scale,
-                            int grad_dtype, void* dz8, void* stream) {
+                            int grad_dtype, float grad_scale, void* dz8, void* stream) {
   if (!dout_nchw || !dz8 || scale < 1) return set_error(FP_ERR_ARG, "fp_heads_bwd: bad argument");
   const long long n = static_cast<long long>(batch) * h * w;
   heads_bwd_kernel<<<nblocks(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      dout_nchw, ch0, reinterpret_cast<const float2*>(head_post), batch, h, w, scale, grad_dtype,
+      dout_nchw, ch0, reinterpret_cast<const float2*>(head_post), batch, h, w, scale, grad_dtype, grad_scale,
       static_cast<uint4*>(dz8));
   FP_CHECK_LAUNCH("fp_heads_bwd");
   return FP_OK;
@@ -751,5 +768,13 @@ extern "C" int fp_adam_step(float* param, const float* grad, float* exp_avg, flo
       param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, static_cast<float>(bc1),
       static_cast<float>(sqrt(bc2)), grad_scale);
   FP_CHECK_LAUNCH("fp_adam_step");
+  return FP_OK;
+}
+
+extern "C" int fp_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                                const float* hyper7_dev, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper7_dev) return set_error(FP_ERR_ARG, "fp_adam_step_dev: bad argument");
+  adam_dev_kernel<<<nblocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, hyper7_dev);
+  FP_CHECK_LAUNCH("fp_adam_step_dev");
   return FP_OK;
 }

@@ -58,9 +58,17 @@ class ConvLayer:
         self.shift = None
 
 
+# layers computed in split precision (hi + lo operand pairs, three-term products) in ``precise`` mode: everything upstream
+# of the low-resolution MASK heads, whose raw logits dominate the output error (scripts/precision_study.py: with this set
+# every output scale lands within 4e-4 of the fp32 reference; splitting only the deep stages does not help because the
+# 16-bit rounding error accumulates evenly over the ~40 layers in front of the '1/8' head)
+PRECISE_PREFIXES = ('stem', 'enc', 'mask.block1', 'mask.block2', 'mask.head1')
+
+
 class Engine:
-    def __init__(self, net, compute_dtype='fp16'):
+    def __init__(self, net, compute_dtype='fp16', precise=False):
         self.net = net
+        self.precise = bool(precise)
         self.lib = _lib.load()
         self.fmt = {'fp16': FP_F16, 'bf16': FP_BF16}[compute_dtype]
         self.tdtype = {FP_F16: torch.float16, FP_BF16: torch.bfloat16}[self.fmt]
@@ -68,6 +76,7 @@ class Engine:
         self._build_layers()
         self._weight_key = None
         self._bufs = {}
+        self.head_tensor_cores = True
         self.launches = 0           # kernels launched through the C ABI (bench.py reports them)
         self.profile = None         # when a list: (kind, layer, flops, start_event, end_event, algorithmic_bytes) per conv launch
         self._prof_open = None
@@ -147,7 +156,9 @@ class Engine:
 
     # ------------------------------------------------------------------------------ weights
     def _param_key(self):
-        key = []
+        # `_weights_epoch` counts the updates the library made through raw pointers (fp_adam_step on the Trainer's flat
+        # buffer, fp_bn_stats on the running statistics): those never bump a tensor's `_version`
+        key = [getattr(self.net, '_weights_epoch', 0)]
         for p in self.net.parameters():
             key.append((p.data_ptr(), p._version))
         for b in self.net.buffers():
@@ -162,8 +173,6 @@ class Engine:
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         dev = self.layers['stem'].weight.device
         for L in self.layers.values():
-            if L.is_head:
-                continue            # heads read the fp32 parameters directly
             w = L.weight.detach()
             if w.dtype != torch.float32 or not w.is_contiguous():
                 w = w.float().contiguous()
@@ -175,6 +184,16 @@ class Engine:
                 cin = L.cin0 + L.cin1
                 _lib.check(self.lib.fp_pack_conv_weight(_ptr(w), L.cout, cin, L.k, L.k, cin, L.npad, L.kpad, self.fmt, 0,
                                                         _ptr(L.w_packed), stream))
+            if self.precise and L.name.startswith(PRECISE_PREFIXES):
+                # [Whi | Whi | Wlo] per tap (fp_conv_fwd_split)
+                if getattr(L, 'w_packed3', None) is None:
+                    L.kpad3 = 768 if L.stem else (3 * L.k * L.k * (L.cin0 + L.cin1) + 63) // 64 * 64
+                    L.w_packed3 = torch.empty((L.npad, L.kpad3), dtype=self.tdtype, device=dev)
+                if L.stem:
+                    _lib.check(self.lib.fp_pack_stem_weight_split(_ptr(w), L.cout, L.npad, self.fmt, _ptr(L.w_packed3), stream))
+                else:
+                    _lib.check(self.lib.fp_pack_conv_weight_split(_ptr(w), L.cout, L.cin0 + L.cin1, L.k, L.k, L.npad, L.kpad3,
+                                                                  self.fmt, _ptr(L.w_packed3), stream))
             if L.bn is not None:
                 # eval-mode BN: y = (x - mean) / sqrt(var + eps) * gamma + beta  (torch BatchNorm2d)
                 bn = L.bn
@@ -224,8 +243,43 @@ class Engine:
         self._prof_end()
         self.launches += 1
 
+    def _conv_split(self, L, src0, src1, out, residual, stream):
+        """Split-precision convolution (fp_conv_fwd_split): src0 / src1 / residual are (hi, lo) pairs or None; out is
+        (hi, lo) -- lo None rounds the output once (fp32 head map or a plain 16-bit tensor)."""
+        s0h, s0l = src0
+        b, h0, w0, c0 = s0h.shape
+        d = FpConvDesc()
+        d.batch, d.c0, d.h0, d.w0, d.up0 = b, c0, h0, w0, L.up0
+        d.c1 = src1[0].shape[3] if src1 is not None else 0
+        d.kh = d.kw = L.k
+        d.stride, d.pad_t, d.pad_l, d.pad_mode = L.stride, L.pad, L.pad, L.pad_mode
+        oh, ol = out
+        d.ho, d.wo = oh.shape[1], oh.shape[2]
+        d.cout, d.kpad, d.npad, d.bn = L.cout, L.kpad3, L.npad, L.bn_tile
+        d.act, d.dtype = L.act, self.fmt
+        d.out_f32 = 1 if L.out_f32 else 0
+        d.out_ld = oh.shape[3]
+        d.res_ld = residual[0].shape[3] if residual is not None else 0
+        d.b_via_tma = 1
+        low = _lib.FpSplitLow(s0l.data_ptr(), src1[1].data_ptr() if src1 is not None else None,
+                              residual[1].data_ptr() if residual is not None else None,
+                              ol.data_ptr() if ol is not None else None)
+        self._prof('fwd', L, b * d.ho * d.wo)
+        _lib.check(self.lib.fp_conv_fwd_split(ctypes.byref(d), _ptr(s0h), _ptr(src1[0]) if src1 is not None else None,
+                                              ctypes.byref(low), _ptr(L.w_packed3), _ptr(L.scale), _ptr(L.shift),
+                                              _ptr(residual[0]) if residual is not None else None, _ptr(oh), stream))
+        self._prof_end()
+        self.launches += 1
+
+    def _pair(self, name, shape):
+        return self._buf(name + '.hi', shape), self._buf(name + '.lo', shape)
+
     def _head(self, L, src, out, stream):
-        """OutConvBlock conv (+ sigmoid): footprints/network.py:174-178."""
+        """OutConvBlock conv (+ sigmoid): footprints/network.py:174-178.  Default: the row-streaming tensor-core kernel
+        with the two output channels padded to N = 16 (the tensor pipe is idle on these HBM-bound layers; one
+        N = 48 instruction per input row, dx and K step); ``head_tensor_cores = False`` selects the CUDA-core kernels."""
+        if self.head_tensor_cores:
+            return self._conv(L, src, None, out, None, stream)
         b, h, w, c = src.shape
         _lib.check(self.lib.fp_head_conv_fwd(_ptr(src), _ptr(L.weight.detach()), _ptr(L.bias.detach()), b, h, w, c,
                                              1 if L.act == FP_ACT_SIGMOID else 0, self.fmt, _ptr(out), stream))
@@ -251,6 +305,8 @@ class Engine:
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         lib = self.lib
 
+        if self.precise:
+            return self._forward_precise(image, stream)
         s2d = self._buf('s2d', (b, h // 2, w // 2, 16))
         _lib.check(lib.fp_stem_prep(_ptr(image), b, h, w, self.fmt, _ptr(s2d), stream))
         f0 = self._buf('f0', (b, h // 2, w // 2, 64))
@@ -304,13 +360,92 @@ class Engine:
             self._head(d['head4'], t2, hd, stream)
             heads[(dname, 4)] = hd
 
+        return self._assemble(heads, b, h, w, image.device, stream)
+
+    def _assemble(self, heads, b, h, w, dev, stream):
         outputs = OrderedDict()
         for hi, key in enumerate(SCALES, start=1):
             scale = (8, 4, 2, 1)[hi - 1]
             # fresh tensors: callers mutate the dict / write into the outputs in place
-            out = torch.empty((b, 4, h, w), dtype=torch.float32, device=image.device)
+            out = torch.empty((b, 4, h, w), dtype=torch.float32, device=dev)
             mh = heads[('mask', hi)]
-            _lib.check(lib.fp_heads_to_nchw(_ptr(mh), _ptr(heads[('depth', hi)]), b, mh.shape[1], mh.shape[2], scale,
-                                            _ptr(out), stream))
+            _lib.check(self.lib.fp_heads_to_nchw(_ptr(mh), _ptr(heads[('depth', hi)]), b, mh.shape[1], mh.shape[2], scale,
+                                                 _ptr(out), stream))
             outputs[key] = out
         return outputs
+
+    def _forward_precise(self, image, stream):
+        """Eval forward with the PRECISE_PREFIXES layers in split precision; everything else as in forward()."""
+        lib = self.lib
+        b, _, h, w = image.shape
+        s2d = self._pair('s2d', (b, h // 2, w // 2, 16))
+        _lib.check(lib.fp_stem_prep_split(_ptr(image), b, h, w, self.fmt, _ptr(s2d[0]), _ptr(s2d[1]), stream))
+        f0 = self._pair('f0', (b, h // 2, w // 2, 64))
+        self._conv_split(self.layers['stem'], s2d, None, f0, None, stream)
+        x = self._pair('pool', (b, h // 4, w // 4, 64))
+        _lib.check(lib.fp_maxpool3x3s2_split(_ptr(f0[0]), _ptr(f0[1]), b, h // 2, w // 2, 64, self.fmt, _ptr(x[0]), _ptr(x[1]),
+                                             stream))
+        feats = [f0]
+        last_li = 0
+        for li, c1, ds, c2 in self.enc_blocks:
+            if li != last_li:
+                feats.append(x)
+                last_li = li
+            hh, ww = x[0].shape[1] // c1.stride, x[0].shape[2] // c1.stride
+            t1 = self._pair(f'{c1.name}.out', (b, hh, ww, c1.cout))
+            self._conv_split(c1, x, None, t1, None, stream)
+            idt = x
+            if ds is not None:
+                idt = self._pair(f'{ds.name}.out', (b, hh, ww, ds.cout))
+                self._conv_split(ds, x, None, idt, None, stream)
+            out = self._pair(f'{c2.name}.out', (b, hh, ww, c2.cout))
+            self._conv_split(c2, t1, None, out, idt, stream)
+            x = out
+        feats.append(x)
+
+        heads = {}
+        for dname in ('mask', 'depth'):
+            d = self.dec[dname]
+            x = feats[4] if dname == 'mask' else feats[4][0]
+            for bi in range(1, 5):
+                split = dname == 'mask' and bi <= 2
+                skip = feats[4 - bi]
+                xs = x[0] if isinstance(x, tuple) else x
+                hh, ww = xs.shape[1], xs.shape[2]
+                co = d[f'b{bi}.pre1'].cout
+                if split:
+                    t = self._pair(f'{dname}.b{bi}.pre1', (b, hh, ww, co))
+                    self._conv_split(d[f'b{bi}.pre1'], x, None, t, None, stream)
+                    t2 = self._pair(f'{dname}.b{bi}.pre2', (b, hh, ww, co))
+                    self._conv_split(d[f'b{bi}.pre2'], t, None, t2, None, stream)
+                    t3 = self._pair(f'{dname}.b{bi}.post1', (b, 2 * hh, 2 * ww, co))
+                    self._conv_split(d[f'b{bi}.post1'], t2, skip, t3, None, stream)
+                    x = self._pair(f'{dname}.b{bi}.post2', (b, 2 * hh, 2 * ww, co))
+                    self._conv_split(d[f'b{bi}.post2'], t3, None, x, None, stream)
+                    if bi == 2:
+                        hd = self._buf(f'{dname}.head1', (b, 2 * hh, 2 * ww, 2), torch.float32)
+                        self._conv_split(d['head1'], x, None, (hd, None), None, stream)
+                        heads[(dname, 1)] = hd
+                    continue
+                xs = x[0] if isinstance(x, tuple) else x          # leaving the precise set: the high halves are the tensor
+                t = self._buf(f'{dname}.b{bi}.pre1', (b, hh, ww, co))
+                self._conv(d[f'b{bi}.pre1'], xs, None, t, None, stream)
+                t2 = self._buf(f'{dname}.b{bi}.pre2', (b, hh, ww, co))
+                self._conv(d[f'b{bi}.pre2'], t, None, t2, None, stream)
+                t3 = self._buf(f'{dname}.b{bi}.post1', (b, 2 * hh, 2 * ww, co))
+                self._conv(d[f'b{bi}.post1'], t2, skip[0], t3, None, stream)
+                x = self._buf(f'{dname}.b{bi}.post2', (b, 2 * hh, 2 * ww, co))
+                self._conv(d[f'b{bi}.post2'], t3, None, x, None, stream)
+                if bi >= 2:
+                    hd = self._buf(f'{dname}.head{bi - 1}', (b, 2 * hh, 2 * ww, 2), torch.float32)
+                    self._head(d[f'head{bi - 1}'], x, hd, stream)
+                    heads[(dname, bi - 1)] = hd
+            hh, ww = x.shape[1], x.shape[2]
+            t = self._buf(f'{dname}.o4.c1', (b, 2 * hh, 2 * ww, 32))
+            self._conv(d['o4.c1'], x, None, t, None, stream)
+            t2 = self._buf(f'{dname}.o4.c2', (b, 2 * hh, 2 * ww, 32))
+            self._conv(d['o4.c2'], t, None, t2, None, stream)
+            hd = self._buf(f'{dname}.head4', (b, 2 * hh, 2 * ww, 2), torch.float32)
+            self._head(d['head4'], t2, hd, stream)
+            heads[(dname, 4)] = hd
+        return self._assemble(heads, b, h, w, image.device, stream)

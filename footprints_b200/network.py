@@ -161,21 +161,24 @@ class FootprintNetwork(nn.Module):
 
     Extra keyword arguments (not in the reference) select the encoder depth and the 16-bit storage
     type of activations/weights inside the kernels: ``compute_dtype`` is ``'fp16'`` (default, 11-bit
-    significand, closest to the reference's fp32) or ``'bf16'``."""
+    significand, closest to the reference's fp32) or ``'bf16'``; ``precise=True`` runs the eval forward's
+    layers upstream of the low-resolution mask heads in split precision (hi + lo 16-bit pairs, three-term
+    tensor-core products) so that ALL four output scales land within 1e-3 of the fp32 reference."""
 
-    def __init__(self, pretrained=True, blocks=(3, 4, 6, 3), compute_dtype='fp16'):
+    def __init__(self, pretrained=True, blocks=(3, 4, 6, 3), compute_dtype='fp16', precise=False):
         super().__init__()
+        self.precise = precise          # eval: split-precision layers upstream of the low-resolution mask heads (engine.py)
         self.encoder = ResnetEncoder(pretrained=pretrained, blocks=blocks)
         self.mask_decoder = SkipDecoder(apply_sigmoid=False)
         self.depth_decoder = SkipDecoder(apply_sigmoid=True)
         self.compute_dtype = compute_dtype
-        self.train_dtype = 'bf16'      # activations in .train() mode; gradients are always bf16
+        self.train_dtype = 'fp16'      # activations AND inter-layer gradients in .train() mode ('fp16' + loss scale, or 'bf16')
         self._engine = None
         self._train_engine = None
 
     def engine(self):
         if self._engine is None:
-            self._engine = Engine(self, self.compute_dtype)
+            self._engine = Engine(self, self.compute_dtype, self.precise)
         return self._engine
 
     def train_engine(self):

@@ -13,7 +13,14 @@ Every arithmetic step is a C-ABI call into ``libfootprints_b200.so``:
             fp_bn_bwd -> fp_conv_wgrad -> fp_conv_fwd(flipped weights [, zero-inserted x2 for the
             stride-2 layers]) with the residual-branch gradient added in the epilogue  (encoder)
 
-Gradients between layers are bf16 (range), parameter gradients fp32.
+Storage types: activations and inter-layer gradients are ONE 16-bit type (``tcgen05.mma kind::f16`` rejects mixed
+f16 x bf16 operands and the weight gradient multiplies the two).  Default ``fp16``: 11-bit significands keep the
+train-mode forward as close to the fp32 reference as the eval path, and a power-of-two LOSS SCALE applied where the
+backward starts (``fp_heads_bwd``) keeps the gradients inside fp16's range -- over the whole network |dZ| spans
+2^-17 .. 2^5 x u, u = 1/(4*B*H*W), on the synthetic batch, i.e. 2^-12 .. 2^10 after the default scale 32/u: normal fp16
+numbers with a 2^6 margin to the top (65504); every 16-bit conversion SATURATES (``cvt.rn.satfinite``), so a gradient
+spike clips element-wise instead of turning into inf - inf = NaN downstream.  Every backward kernel is linear in that
+tensor and the fp32 parameter gradients are un-scaled exactly (power of two) by the optimiser / the autograd glue.  ``bf16`` (scale 1) remains selectable.  Parameter gradients are fp32.
 """
 import ctypes
 from collections import OrderedDict
@@ -21,7 +28,9 @@ from collections import OrderedDict
 import torch
 
 from . import _lib
-from ._lib import FP_ACT_ELU, FP_ACT_NONE, FP_ACT_RELU, FP_BF16, FP_PAD_ZERO, FpConvDesc
+import math
+
+from ._lib import FP_ACT_ELU, FP_ACT_NONE, FP_ACT_RELU, FP_BF16, FP_F16, FP_PAD_ZERO, FpConvDesc
 from .engine import SCALES, Engine, _bn_tile, _ptr
 
 _RAW = object()   # sentinel: run the conv with no scale/shift (NULL pointers)
@@ -29,12 +38,12 @@ _RAW = object()   # sentinel: run the conv with no scale/shift (NULL pointers)
 
 class TrainEngine(Engine):
 
-    def __init__(self, net, compute_dtype='bf16'):
+    def __init__(self, net, compute_dtype='fp16'):
         super().__init__(net, compute_dtype)
-        self.gfmt = FP_BF16
-        self.gdtype = torch.bfloat16
-        self._bn_state = {}
-        self._saved = None
+        self.gfmt = self.fmt                 # gradients share the activations' 16-bit type (see the module docstring)
+        self.gdtype = self.tdtype
+        self.loss_scale = None               # None: 2^k ~ 32 * 4*B*H*W for fp16 gradients, 1 for bf16; or a fixed float
+        self.grad_scale = 1.0                # scale of the parameter gradients the last backward() produced
         self._red_ws = None
         self._wg_ws = None
         self._loss_ws = None
@@ -73,31 +82,50 @@ class TrainEngine(Engine):
         d.b_via_tma = 1
         return d
 
-    def refresh_weights(self, force=False):
-        """Training: weights change every step, so pack unconditionally (forward and flipped)."""
-        stream = self._stream()
+    def _pack_plan(self):
+        """Device table of FpPackJob records: forward and rotated (data-gradient) packing of every convolution weight.
+        Rebuilt only when a parameter moved (the Trainer re-points them into its flat buffer once)."""
+        convs = list(self.layers.values())        # heads too: their forward runs on the tensor-core kernel (N padded to 16)
+        key = tuple(L.weight.data_ptr() for L in convs)
+        if getattr(self, '_pack_key', None) == key:
+            return
         dev = self._dev()
-        for L in self.layers.values():
-            if L.is_head:
-                continue            # heads read the fp32 parameters directly
+        jobs, first = [], 0
+        for L in convs:
             w = L.weight.detach()
+            cin = L.cin0 + L.cin1
             if L.w_packed is None:
                 L.w_packed = torch.empty((L.npad, L.kpad), dtype=self.tdtype, device=dev)
-            cin = L.cin0 + L.cin1
             if L.stem:
-                _lib.check(self.lib.fp_pack_stem_weight(_ptr(w), L.cout, L.npad, self.fmt, _ptr(L.w_packed), stream))
-            else:
-                _lib.check(self.lib.fp_pack_conv_weight(_ptr(w), L.cout, cin, L.k, L.k, cin, L.npad, L.kpad, self.fmt, 0,
-                                                        _ptr(L.w_packed), stream))
-                # data-gradient operand: rows = cin, K = taps * cout_pad, filter rotated by 180 degrees
-                if getattr(L, 'w_flip', None) is None:
-                    L.cpad_out = max(8, L.cout)
-                    L.d_bn = _bn_tile(cin)
-                    L.d_npad = (cin + L.d_bn - 1) // L.d_bn * L.d_bn
-                    L.d_kpad = (L.k * L.k * L.cpad_out + 63) // 64 * 64
-                    L.w_flip = torch.empty((L.d_npad, L.d_kpad), dtype=self.gdtype, device=dev)
-                _lib.check(self.lib.fp_pack_conv_weight(_ptr(w), L.cout, cin, L.k, L.k, L.cpad_out, L.d_npad, L.d_kpad,
-                                                        self.gfmt, 1, _ptr(L.w_flip), stream))
+                jobs.append(_lib.FpPackJob(w.data_ptr(), L.w_packed.data_ptr(), L.cout, 3, 7, 7, 16, L.npad, 256, self.fmt, 0, 1, first))
+                first += L.npad * 256
+                continue
+            jobs.append(_lib.FpPackJob(w.data_ptr(), L.w_packed.data_ptr(), L.cout, cin, L.k, L.k, cin, L.npad, L.kpad,
+                                       self.fmt, 0, 0, first))
+            first += L.npad * L.kpad
+            if L.is_head:
+                continue            # the heads' data gradient runs on the CUDA-core kernel (fp32 parameters)
+            # data-gradient operand: rows = cin, K = taps * cout_pad, filter rotated by 180 degrees
+            if getattr(L, 'w_flip', None) is None:
+                L.cpad_out = max(8, L.cout)
+                L.d_bn = _bn_tile(cin)
+                L.d_npad = (cin + L.d_bn - 1) // L.d_bn * L.d_bn
+                L.d_kpad = (L.k * L.k * L.cpad_out + 63) // 64 * 64
+                L.w_flip = torch.empty((L.d_npad, L.d_kpad), dtype=self.gdtype, device=dev)
+            jobs.append(_lib.FpPackJob(w.data_ptr(), L.w_flip.data_ptr(), L.cout, cin, L.k, L.k, L.cpad_out, L.d_npad,
+                                       L.d_kpad, self.gfmt, 1, 0, first))
+            first += L.d_npad * L.d_kpad
+        arr = (_lib.FpPackJob * len(jobs))(*jobs)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self._pack_table = host.to(dev)
+        self._pack_n, self._pack_total, self._pack_key = len(jobs), first, key
+
+    def refresh_weights(self, force=False):
+        """Training: weights change every step, so every operand is re-packed -- ONE launch for all of them."""
+        self._pack_plan()
+        _lib.check(self.lib.fp_pack_weights_batched(_ptr(self._pack_table), self._pack_n, self._pack_total, self._stream()))
+        self.launches += 1
+        for L in self.layers.values():
             L.scale = None
             L.shift = L.bias.detach() if L.bias is not None else None
         self._weight_key = None
@@ -109,10 +137,9 @@ class TrainEngine(Engine):
         ho, wo = (h // L.stride, w // L.stride) if not L.stem else (h, w)
         z = torch.empty((b, ho, wo, L.cout), dtype=self.tdtype, device=src.device)
         self._conv(L, src, None, z, None, stream, scale=_RAW, shift=_RAW, act=FP_ACT_NONE)
-        st = self._bn_state.get(L.name)
-        if st is None:
-            st = {k: torch.empty(L.cout, dtype=torch.float32, device=src.device) for k in ('scale', 'shift', 'mean', 'invstd')}
-            self._bn_state[L.name] = st
+        # batch statistics belong to THIS forward (a second forward before the backward must not overwrite them)
+        stv = torch.empty((4, L.cout), dtype=torch.float32, device=src.device)
+        st = {'scale': stv[0], 'shift': stv[1], 'mean': stv[2], 'invstd': stv[3]}
         bn = L.bn
         M = b * ho * wo
         _lib.check(self.lib.fp_bn_stats(_ptr(z), M, L.cout, self.fmt, _ptr(bn.weight.detach()), _ptr(bn.bias.detach()),
@@ -122,8 +149,8 @@ class TrainEngine(Engine):
         y = torch.empty_like(z)
         _lib.check(self.lib.fp_bn_apply(_ptr(z), _ptr(st['scale']), _ptr(st['shift']), _ptr(residual), 1 if relu else 0, M,
                                         L.cout, self.fmt, _ptr(y), stream))
-        bn.num_batches_tracked += 1
         saved[L.name] = (src, z, y)
+        saved['bn'][L.name] = st
         return y
 
     def _conv(self, L, src0, src1, out, residual, stream, scale=None, shift=None, act=None):
@@ -138,9 +165,11 @@ class TrainEngine(Engine):
         else:
             super()._conv(L, src0, src1, out, residual, stream, scale, shift, act)
 
-    def forward_train(self, image):
-        """Train-mode forward (footprints/network.py:21-30 with BatchNorm in training mode).  Returns the
-        dict of four fp32 NCHW outputs and keeps what the backward needs."""
+    def forward_train(self, image, save=True):
+        """Train-mode forward (footprints/network.py:21-30 with BatchNorm in training mode).  Returns
+        ``(outputs, saved)``: the dict of four fp32 NCHW outputs and everything the backward of THIS forward needs
+        (activations, per-layer batch statistics) -- the caller keeps ``saved`` (the autograd node's ctx, or the
+        Trainer) and hands it to ``backward``; ``save=False`` (no gradient wanted) keeps nothing alive."""
         _lib.require_device()
         b, _, h, w = image.shape
         if h % 32 or w % 32:
@@ -150,7 +179,7 @@ class TrainEngine(Engine):
         stream = self._stream()
         lib = self.lib
         dev = image.device
-        sv = {}
+        sv = {'bn': {}}
 
         def new(shape, dtype=None):
             return torch.empty(shape, dtype=dtype or self.tdtype, device=dev)
@@ -222,8 +251,10 @@ class TrainEngine(Engine):
             outputs[key] = out
         sv['s2d'] = s2d
         sv['shape'] = (b, h, w)
-        self._saved = sv
-        return outputs
+        # torchvision BatchNorm2d bookkeeping (num_batches_tracked += 1 per BN per forward): one multi-tensor launch
+        torch._foreach_add_([L.bn.num_batches_tracked for L in self.layers.values() if L.bn is not None], 1)
+        self.net._weights_epoch = getattr(self.net, '_weights_epoch', 0) + 1      # running statistics changed (raw pointers)
+        return outputs, (sv if save else None)
 
     # ------------------------------------------------------------------------------ backward pieces
     def _wgrad(self, L, src0, src1, dz, grads, stream):
@@ -302,9 +333,9 @@ class TrainEngine(Engine):
         _lib.check(self.lib.fp_fold_bwd(_ptr(dvp), b, hv, wv, dvp.shape[3], coff, c, 1 if up else 0, 1 if accumulate else 0,
                                         _ptr(y_act), act, self.fmt, self.gfmt, _ptr(dst), stream))
 
-    def _bn_bwd(self, L, dy, relu, want_g, grads, stream):
-        src, z, y = self._saved[L.name]
-        st = self._bn_state[L.name]
+    def _bn_bwd(self, sv, L, dy, relu, want_g, grads, stream):
+        src, z, y = sv[L.name]
+        st = sv['bn'][L.name]
         b, ho, wo, c = z.shape
         dz = torch.empty(z.shape, dtype=self.gdtype, device=z.device)
         g = torch.empty(z.shape, dtype=self.gdtype, device=z.device) if want_g else None
@@ -319,12 +350,19 @@ class TrainEngine(Engine):
         return dz, g
 
     # ------------------------------------------------------------------------------ backward
-    def backward(self, douts):
-        """douts: {'1/8','1/4','1/2','1/1'} -> d(loss)/d(output) fp32 [B,4,H,W].  Returns {parameter: fp32 grad}."""
-        sv = self._saved
+    def backward(self, douts, sv):
+        """douts: {'1/8','1/4','1/2','1/1'} -> d(loss)/d(output) fp32 [B,4,H,W].  Returns {parameter: fp32 grad}; the
+        gradients are multiplied by ``self.grad_scale`` (the loss scale; a power of two) -- the caller divides it out."""
         if sv is None:
-            raise RuntimeError('backward() without a preceding forward_train()')
+            raise RuntimeError('backward() needs the saved state forward_train() returned')
         b, h, w = sv['shape']
+        if self.loss_scale is not None:
+            gs = float(self.loss_scale)
+        elif self.gfmt == FP_F16:
+            gs = 2.0 ** round(math.log2(32.0 * 4.0 * b * h * w))
+        else:
+            gs = 1.0
+        self.grad_scale = gs
         stream = self._stream()
         lib = self.lib
         dev = self._dev()
@@ -346,7 +384,7 @@ class TrainEngine(Engine):
                 hh, ww = hd.shape[1], hd.shape[2]
                 dz = gnew((b, hh, ww, 8))
                 _lib.check(lib.fp_heads_bwd(_ptr(douts[SCALES[hi - 1]]), ch0, _ptr(hd) if sigmoid else None, b, hh, ww,
-                                            h // hh, self.gfmt, _ptr(dz), stream))
+                                            h // hh, self.gfmt, gs, _ptr(dz), stream))
                 return L, src, dz
 
             def conv_bwd(L, dz):
@@ -431,15 +469,15 @@ class TrainEngine(Engine):
         for idx in range(len(self.enc_blocks) - 1, -1, -1):
             li, c1, ds, c2 = self.enc_blocks[idx]
             x_in = sv[c1.name][0]
-            dz2, g = self._bn_bwd(c2, dy, True, True, grads, stream)
+            dz2, g = self._bn_bwd(sv, c2, dy, True, True, grads, stream)
             t1 = sv[c2.name][0]
             self._wgrad(c2, t1, None, dz2, grads, stream)
             dt1 = self._dgrad_plain(c2, dz2, (t1.shape[1], t1.shape[2]), None, stream)
-            dz1, _ = self._bn_bwd(c1, dt1, True, False, grads, stream)
+            dz1, _ = self._bn_bwd(sv, c1, dt1, True, False, grads, stream)
             self._wgrad(c1, x_in, None, dz1, grads, stream)
             first_of_stage = idx == 0 or self.enc_blocks[idx - 1][0] != li
             if ds is not None:
-                dzd, _ = self._bn_bwd(ds, g, False, False, grads, stream)
+                dzd, _ = self._bn_bwd(sv, ds, g, False, False, grads, stream)
                 self._wgrad(ds, x_in, None, dzd, grads, stream)
                 # the block input is the previous stage's feature: add the decoders' contribution here
                 extra = dfeat[li] if first_of_stage else None
@@ -455,7 +493,6 @@ class TrainEngine(Engine):
         _lib.check(lib.fp_maxpool3x3s2_bwd(_ptr(f0), _ptr(dy), b, f0.shape[1], f0.shape[2], 64, self.fmt, self.gfmt, 1,
                                            _ptr(dfeat[0]), stream))
         stem = self.layers['stem']
-        dz0, _ = self._bn_bwd(stem, dfeat[0], True, False, grads, stream)
+        dz0, _ = self._bn_bwd(sv, stem, dfeat[0], True, False, grads, stream)
         self._wgrad(stem, sv['s2d'], None, dz0, grads, stream)
-        self._saved = None
         return grads

@@ -76,6 +76,33 @@ typedef struct FpConvDesc {
 int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* src1, const void* w_packed,
                 const float* scale, const float* shift, const void* residual, void* out, void* stream);
 
+/* Split-precision variant ("precise" mode; closes the gap between 16-bit tensor-core operands and the reference's fp32
+ * arithmetic on the layers upstream of the low-resolution heads).  Every activation is a PAIR of 16-bit tensors
+ * hi + lo (hi = round16(y), lo = round16(y - hi): ~22 significant bits), weights likewise, and the product is the
+ * three-term expansion  A*W ~ Ahi*Whi + Alo*Whi + Ahi*Wlo  accumulated in fp32 in ONE implicit GEMM whose K axis per
+ * filter tap is [hi(src0,src1) | lo(src0,src1) | hi(src0,src1)] against weights [Whi | Whi | Wlo]
+ * (fp_pack_conv_weight_split; kpad >= 3*kh*kw*(c0+c1)).  `low` carries the low halves; out_lo == NULL rounds the
+ * output once (a plain 16-bit or fp32 tensor for a consumer outside the precise set).  Same gather semantics and epilogue
+ * as fp_conv_fwd (general kernel only). */
+typedef struct FpSplitLow {
+  const void* src0_lo;
+  const void* src1_lo;
+  const void* residual_lo;
+  void* out_lo;
+} FpSplitLow;
+int fp_conv_fwd_split(const FpConvDesc* d, const void* src0_hi, const void* src1_hi, const FpSplitLow* low,
+                      const void* w_packed3, const float* scale, const float* shift, const void* residual_hi,
+                      void* out_hi, void* stream);
+/* [npad][kpad] with K index = tap*3*cin + part*cin + c: part 0,1 -> round16(w), part 2 -> round16(w - round16(w)). */
+int fp_pack_conv_weight_split(const float* w_oihw, int cout, int cin, int kh, int kw, int npad, int kpad, int dtype,
+                              void* w_packed3, void* stream);
+/* stem (space-to-depth 4x4 taps x 16 channels): K index = tap*48 + part*16 + ch, kpad = 768. */
+int fp_pack_stem_weight_split(const float* w_oihw, int cout, int npad, int dtype, void* w_packed3, void* stream);
+/* fp_stem_prep / fp_maxpool3x3s2 on hi + lo pairs. */
+int fp_stem_prep_split(const float* image_nchw, int batch, int h, int w, int dtype, void* out_hi, void* out_lo, void* stream);
+int fp_maxpool3x3s2_split(const void* in_hi, const void* in_lo, int batch, int h, int w, int c, int dtype, void* out_hi,
+                          void* out_lo, void* stream);
+
 /* OIHW fp32 -> packed [npad][kpad] 16-bit, K index = (ky*kw + kx)*cpad + c (tap-major, channel-minor),
  * zero padded; cpad >= the channel-minor extent (cin, or cout when flipped) is the channel count of the
  * tensor the kernel will gather (a power of two >= 8 together with a concat partner).  flip=1 packs the
@@ -84,6 +111,18 @@ int fp_conv_fwd(const FpConvDesc* d, const void* src0, const void* src1, const v
  * descriptors of fp_conv_fwd expect. */
 int fp_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw, int cpad, int npad, int kpad,
                         int dtype, int flip, void* w_packed, void* stream);
+
+/* All weight operands of a network in ONE launch (training re-packs ~142 of them every step; §8 f1: this launch follows
+ * fp_adam_step in the optimiser pass).  jobs_dev: device array sorted by `first`; job i produces packed elements
+ * [first_i, first_{i+1}) of the concatenated output index space (`total` = end of the last job) with the semantics of
+ * fp_pack_conv_weight (stem = 0) or fp_pack_stem_weight (stem = 1: kpad is 256, cpad / kh / kw / flip unused). */
+typedef struct FpPackJob {
+  const float* w;     /* OIHW fp32 parameter                      */
+  void* out;          /* packed [npad][kpad] 16-bit               */
+  int32_t cout, cin, kh, kw, cpad, npad, kpad, dtype, flip, stem;
+  int64_t first;
+} FpPackJob;
+int fp_pack_weights_batched(const FpPackJob* jobs_dev, int njobs, long long total, void* stream);
 
 /* Stem weight [64][3][7][7] -> packed [npad][256] for the space-to-depth formulation: the 7x7/2 conv
  * (torchvision resnet.py:197) equals a 4x4/1 conv over 2x2 space-to-depth blocks of 16 channels
@@ -161,9 +200,11 @@ int fp_loss_fwd_bwd(const float* const* pred, float* const* grad, const float* d
 
 /* Adjoint of fp_heads_to_nchw for one decoder: channels [ch0, ch0+2) of dout [B][4][H][W] -> gradient of the head
  * convolution's pre-upsample output [B][h][w][8] (channels 2..7 zero), times sigmoid' when head_post (the saved
- * post-sigmoid head map) is given (network.py:177-181). */
+ * post-sigmoid head map) is given (network.py:177-181).  grad_scale multiplies the result: the loss scale that keeps
+ * FP_F16 inter-layer gradients inside fp16's range (every later backward kernel is linear in this tensor; the optimiser
+ * divides it out of the fp32 parameter gradients); 1 for FP_BF16 gradients. */
 int fp_heads_bwd(const float* dout_nchw, int ch0, const float* head_post, int batch, int h, int w, int scale,
-                 int grad_dtype, void* dz8, void* stream);
+                 int grad_dtype, float grad_scale, void* dz8, void* stream);
 
 /* Adjoint of [nearest x2] -> [concat] -> [ReflectionPad2d(1)] (network.py:154-155,115): folds the gradient of the
  * padded virtual input dvp [B][hv+2][wv+2][ccat] (produced by fp_conv_fwd run as a zero-padded full correlation
@@ -193,6 +234,11 @@ int fp_conv_wgrad(const FpConvDesc* d, const void* src0, const void* src1, const
  * grad_scale multiplies the gradient first (1/world_size after a summing all-reduce). */
 int fp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                  float beta2, float eps, int step, float grad_scale, void* stream);
+/* The same update with the per-step scalars in DEVICE memory: hyper7_dev = {lr, beta1, beta2, eps, 1 - beta1^step,
+ * sqrt(1 - beta2^step), grad_scale}.  For a CUDA-graph-captured training step (kernel arguments are baked into a graph;
+ * the host refreshes these seven floats before each replay -- StepLR, bias correction). */
+int fp_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                     const float* hyper7_dev, void* stream);
 
 /* perf triage only: clock stamps recorded by CTA 0 of the last fp_conv_fwd when FP_DEBUG_FLAGS & 16 */
 int fp_debug_read_trace(long long* out_3x2048);

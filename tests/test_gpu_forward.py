@@ -171,3 +171,90 @@ def test_matterport_shape_512x640_resnet18():
         assert out[k].shape == (2, 4, 512, 640)
         err = (out[k].cpu() - ref[k]).abs().max().item()
         assert err <= TOL['fp16'][k], (k, err)
+
+
+def _split16(t):
+    hi = t.half()
+    lo = (t - hi.float()).half()
+    return hi, lo
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(c0=64, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=0, cout=64, act=1, res=True),      # BasicBlock conv2 + residual
+    dict(c0=64, c1=0, up0=0, k=3, stride=2, pad=1, pad_mode=0, cout=128, act=1, res=False),    # stride-2 stage entry
+    dict(c0=64, c1=0, up0=0, k=1, stride=2, pad=0, pad_mode=0, cout=128, act=0, res=False),    # 1x1 downsample
+    dict(c0=128, c1=128, up0=1, k=3, stride=1, pad=1, pad_mode=1, cout=128, act=2, res=False), # upsample + concat + reflect
+    dict(c0=128, c1=0, up0=0, k=3, stride=1, pad=1, pad_mode=1, cout=2, act=0, res=False),     # head (fp32 out, no lo)
+])
+def test_split_precision_conv_matches_torch_fp64(cfg):
+    """fp_conv_fwd_split on UNROUNDED fp32 operands (each carried as a hi + lo fp16 pair) against torch's fp32 convolution:
+    the three-term product leaves ~2^-21 relative error, 500x below a single 16-bit pass."""
+    lib = _lib.load()
+    _lib.require_device()
+    g = torch.Generator().manual_seed(5)
+    b, h0, w0 = 2, 12, 20
+    hin, win = (2 * h0, 2 * w0) if cfg['up0'] else (h0, w0)
+    cin, k, cout = cfg['c0'] + cfg['c1'], cfg['k'], cfg['cout']
+    x0 = torch.randn(b, cfg['c0'], h0, w0, generator=g).cuda()
+    x1 = torch.randn(b, cfg['c1'], hin, win, generator=g).cuda() if cfg['c1'] else None
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    bias = (torch.randn(cout, generator=g) * 0.1).cuda()
+    ho = (hin + 2 * cfg['pad'] - k) // cfg['stride'] + 1
+    wo = (win + 2 * cfg['pad'] - k) // cfg['stride'] + 1
+    res = torch.randn(b, cout, ho, wo, generator=g).cuda() if cfg['res'] else None
+    # reference in float64 (torch's fp32 CUDA convolutions default to TF32 tensor cores: 10-bit significands)
+    xin = F.interpolate(x0.double(), scale_factor=2, mode='nearest') if cfg['up0'] else x0.double()
+    if x1 is not None:
+        xin = torch.cat([xin, x1.double()], 1)
+    if cfg['pad_mode'] == 1:
+        ref = F.conv2d(F.pad(xin, (1, 1, 1, 1), mode='reflect'), w.double(), bias.double(), stride=cfg['stride'])
+    else:
+        ref = F.conv2d(xin, w.double(), bias.double(), stride=cfg['stride'], padding=cfg['pad'])
+    if res is not None:
+        ref = ref + res.double()
+    ref = {0: lambda t: t, 1: F.relu, 2: F.elu}[cfg['act']](ref).float()
+
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    s0 = _split16(nhwc(x0))
+    s1 = _split16(nhwc(x1)) if x1 is not None else None
+    r = _split16(nhwc(res)) if res is not None else None
+    bn_tile = 16 if cout <= 16 else (64 if cout <= 64 else 128)
+    npad = (cout + bn_tile - 1) // bn_tile * bn_tile
+    kpad = (3 * k * k * cin + 63) // 64 * 64
+    wp = torch.empty(npad, kpad, dtype=torch.float16, device='cuda')
+    _lib.check(lib.fp_pack_conv_weight_split(w.data_ptr(), cout, cin, k, k, npad, kpad, 0, wp.data_ptr(), None))
+    head = cout == 2
+    out_hi = torch.empty(b, ho, wo, cout, dtype=torch.float32 if head else torch.float16, device='cuda')
+    out_lo = None if head else torch.empty_like(out_hi)
+    d = FpConvDesc(batch=b, c0=cfg['c0'], h0=h0, w0=w0, up0=cfg['up0'], c1=cfg['c1'], kh=k, kw=k, stride=cfg['stride'],
+                   pad_t=cfg['pad'], pad_l=cfg['pad'], pad_mode=cfg['pad_mode'], ho=ho, wo=wo, cout=cout, kpad=kpad, npad=npad,
+                   bn=bn_tile, act=cfg['act'], dtype=0, out_f32=1 if head else 0, out_ld=cout, res_ld=cout if res is not None else 0,
+                   b_via_tma=1)
+    low = _lib.FpSplitLow(s0[1].data_ptr(), s1[1].data_ptr() if s1 else None, r[1].data_ptr() if r else None,
+                          out_lo.data_ptr() if out_lo is not None else None)
+    _lib.check(lib.fp_conv_fwd_split(ctypes.byref(d), s0[0].data_ptr(), s1[0].data_ptr() if s1 else None, ctypes.byref(low),
+                                     wp.data_ptr(), None, bias.data_ptr(), r[0].data_ptr() if r else None,
+                                     out_hi.data_ptr(), None))
+    torch.cuda.synchronize()
+    got = out_hi.float() + (out_lo.float() if out_lo is not None else 0)
+    err = (got.permute(0, 3, 1, 2) - ref).abs().max().item()
+    print(f'split conv {cfg}: max abs err vs torch fp64 {err:.2e} (|ref| max {ref.abs().max().item():.2f})')
+    assert err <= 2e-5 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize('trained_like,shape', [(True, (1, 192, 640)), (False, (1, 192, 640)), (True, (2, 64, 96))])
+def test_precise_mode_meets_1e_3_on_every_scale(trained_like, shape):
+    """``FootprintNetwork(precise=True)``: the layers upstream of the low-resolution mask heads in split precision --
+    all FOUR output scales within the north star's 1e-3 of the fp32 reference (trained-like and random-init weights)."""
+    sd = synthetic_state_dict('resnet34', 0, trained_like=trained_like)
+    net = FootprintNetwork(pretrained=False, precise=True)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    data = synthetic_batch(*shape, 1)
+    out = net(data['image'].cuda())
+    with torch.no_grad():
+        ref = O.network_forward(sd, data['image'], 'resnet34', training=False)
+    for k in out:
+        err = (out[k].cpu() - ref[k]).abs().max().item()
+        print(f'precise eval trained_like={trained_like} {shape} scale {k}: max abs err {err:.3e} (bar 1e-03)')
+        assert err <= 1e-3, (k, err)

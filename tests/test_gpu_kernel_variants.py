@@ -188,3 +188,44 @@ def test_wgrad_roll_matches_default_and_autograd(cfg):
     tol = 2e-3 * wgt.grad.abs().max().item() + 1e-4
     assert (outs['0'] - wgt.grad).abs().max().item() <= tol
     assert (outs['1'] - wgt.grad).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(c=32, h=20, w=256, b=2, sigmoid=1),       # head4-class: CB 32
+    dict(c=64, h=12, w=160, b=2, sigmoid=0),       # head2/3-class: CB 64, 62.5 %-used segments
+    dict(c=128, h=7, w=80, b=3, sigmoid=1),        # head1-class: two channel blocks, ragged item
+])
+def test_rowstream_head_n16_matches_cuda_core_head_and_torch(cfg):
+    """The 2-channel heads on the tensor-core row-streaming kernel (N padded to 16, fp32 NHWC [.,.,.,2] output,
+    bias + optional sigmoid in the epilogue) against the CUDA-core head kernel and torch."""
+    lib = _lib.load()
+    _lib.require_device()
+    g = torch.Generator().manual_seed(21)
+    b, h, w, c = cfg['b'], cfg['h'], cfg['w'], cfg['c']
+    x = torch.randn(b, c, h, w, generator=g).to(DT).float().cuda()
+    wgt = ((torch.rand(2, c, 3, 3, generator=g) * 2 - 1) / (9 * c) ** 0.5).cuda()
+    bias = (torch.randn(2, generator=g) * 0.1).cuda()
+    ref = F.conv2d(F.pad(x, (1, 1, 1, 1), mode='reflect'), wgt.to(DT).float(), bias)
+    if cfg['sigmoid']:
+        ref = torch.sigmoid(ref)
+    kpad = (9 * c + 63) // 64 * 64
+    wp = torch.empty(16, kpad, dtype=DT, device='cuda')
+    _lib.check(lib.fp_pack_conv_weight(P(wgt), 2, c, 3, 3, c, 16, kpad, BF, 0, P(wp), None))
+    d = FpConvDesc(batch=b, c0=c, h0=h, w0=w, up0=0, c1=0, kh=3, kw=3, stride=1, pad_t=1, pad_l=1, pad_mode=1, ho=h, wo=w,
+                   cout=2, kpad=kpad, npad=16, bn=16, act=3 if cfg['sigmoid'] else 0, dtype=BF, out_f32=1, out_ld=2,
+                   res_ld=0, b_via_tma=1, w_dtype_plus1=0)
+    xs = x.permute(0, 2, 3, 1).contiguous().to(DT)
+    outs = {}
+    for mode in ('1', '0'):            # row-streaming N = 16 kernel / general kernel<16>
+        with _Env(FP_ROWSTREAM=mode):
+            y = torch.full((b, h, w, 2), float('nan'), dtype=torch.float32, device='cuda')
+            _lib.check(lib.fp_conv_fwd(ctypes.byref(d), P(xs), None, P(wp), None, P(bias), None, P(y), None))
+            torch.cuda.synchronize()
+            outs[mode] = y.permute(0, 3, 1, 2)
+    yc = torch.empty((b, h, w, 2), dtype=torch.float32, device='cuda')
+    _lib.check(lib.fp_head_conv_fwd(P(xs), P(wgt), P(bias), b, h, w, c, cfg['sigmoid'], BF, P(yc), None))
+    torch.cuda.synchronize()
+    for name, got in (('rowstream', outs['1']), ('general', outs['0'])):
+        assert torch.isfinite(got).all(), name
+        assert (got - ref).abs().max().item() <= 5e-4, (name, (got - ref).abs().max().item())
+    assert (yc.permute(0, 3, 1, 2) - outs['1']).abs().max().item() <= 5e-3      # CUDA-core kernel keeps fp32 weights

@@ -15,6 +15,15 @@ BF = 1  # FP_BF16
 DT = torch.bfloat16
 
 
+@pytest.fixture(autouse=True, params=['bf16', 'fp16'])
+def _storage_type(request):
+    """Every kernel test runs for both 16-bit storage types (training defaults to fp16 + loss scale; bf16 selectable)."""
+    global BF, DT
+    BF, DT = (1, torch.bfloat16) if request.param == 'bf16' else (0, torch.float16)
+    yield
+    BF, DT = 1, torch.bfloat16
+
+
 def P(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -132,9 +141,10 @@ def test_heads_backward(lib, scale, sigmoid):
     out.backward(dout_full[:, ch0:ch0 + 2])
     head_post = post.detach().permute(0, 2, 3, 1).contiguous()
     dz = torch.empty(b, h, w, 8, dtype=DT, device='cuda')
-    _lib.check(lib.fp_heads_bwd(P(dout_full), ch0, P(head_post) if sigmoid else None, b, h, w, scale, BF, P(dz), None))
+    gs = 0.25 * scale                 # the loss scale (a power of two) multiplies the result exactly
+    _lib.check(lib.fp_heads_bwd(P(dout_full), ch0, P(head_post) if sigmoid else None, b, h, w, scale, BF, gs, P(dz), None))
     torch.cuda.synchronize()
-    got = dz.float()[..., :2].permute(0, 3, 1, 2)
+    got = dz.float()[..., :2].permute(0, 3, 1, 2) / gs
     assert (got - pre.grad).abs().max() <= 1e-2 * pre.grad.abs().max() + 1e-6
     assert dz.float()[..., 2:].abs().max() == 0
 
