@@ -37,6 +37,7 @@ def parse():
     ap.add_argument('--arch', default='resnet34', choices=['resnet34', 'resnet18'])
     ap.add_argument('--mode', default='train', choices=['train', 'infer'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precise', action='store_true', help='split-precision layers upstream of the low-resolution mask heads (all four output scales within 1e-3 of the fp32 reference)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying the CUDA graph of the step')
     return ap.parse_args()
 
@@ -169,7 +170,7 @@ def main():
         pg = dist.group.WORLD
     blocks = {'resnet34': (3, 4, 6, 3), 'resnet18': (2, 2, 2, 2)}[args.arch]
     torch.manual_seed(0)
-    net = FootprintNetwork(pretrained=False, blocks=blocks).cuda()
+    net = FootprintNetwork(pretrained=False, blocks=blocks, precise=args.precise).cuda()
     B = args.batch
     data = synthetic_batch(B, H, W, seed=1 + rank)
     host = {k: v.pin_memory() for k, v in data.items()}

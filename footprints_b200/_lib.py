@@ -60,6 +60,8 @@ PROTOTYPES = {
     'fp_head_conv_wgrad': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     'fp_reduce_workspace_floats': (ctypes.c_int, [_i32]),
     'fp_bn_stats': (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'fp_bn_stats_split': (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'fp_bn_apply_split': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     'fp_bn_apply': (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
     'fp_bn_bwd': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     'fp_bias_grad': (ctypes.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),

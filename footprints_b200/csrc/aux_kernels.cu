@@ -16,6 +16,16 @@ __device__ __forceinline__ uint16_t to16(float v, int fmt) {
   return static_cast<uint16_t>(fp::f32x2_to_f16x2_sat(v, 0.f) & 0xFFFFu);
 }
 
+__device__ __forceinline__ float from16(uint16_t u, int fmt) {
+  if (fmt == FP_BF16) return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
+  return __half2float(*reinterpret_cast<__half*>(&u));
+}
+// v -> (hi, lo) with hi = round16(v), lo = round16(v - hi)
+__device__ __forceinline__ void split16(float v, int fmt, uint16_t& hi, uint16_t& lo) {
+  hi = to16(v, fmt);
+  lo = to16(v - from16(hi, fmt), fmt);
+}
+
 // ---------------------------------------------------------------------------------- weight packing
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int kh, int kw, int cpad,
                                         int npad, int kpad, int fmt, int flip, uint16_t* __restrict__ out) {
@@ -65,6 +75,28 @@ __global__ void pack_batched_kernel(const FpPackJob* __restrict__ jobs, int njob
   const float* __restrict__ w = j.w;
   uint16_t* __restrict__ out = static_cast<uint16_t*>(j.out);
   float v = 0.f;
+  if (j.flip == 2) {                  // split precision: K index = tap*3*cg + part*cg + c, part 2 carries the low halves
+    const int n = static_cast<int>(local / j.kpad);
+    const int k = static_cast<int>(local - static_cast<long long>(n) * j.kpad);
+    const int cg = j.stem ? 16 : j.cin;
+    const int tap = k / (3 * cg);
+    const int r = k - tap * 3 * cg;
+    const int part = r / cg;
+    const int c = r - part * cg;
+    if (j.stem) {
+      const int bh = tap >> 2, bw = tap & 3;
+      const int sub = c >> 2, ci = c & 3;
+      const int ky = 2 * bh + (sub >> 1) - 1, kx = 2 * bw + (sub & 1) - 1;
+      if (n < j.cout && tap < 16 && ci < 3 && ky >= 0 && ky < 7 && kx >= 0 && kx < 7) v = w[((n * 3 + ci) * 7 + ky) * 7 + kx];
+    } else if (n < j.cout && tap < j.kh * j.kw) {
+      const int ky = tap / j.kw, kx = tap - ky * j.kw;
+      v = w[((static_cast<long long>(n) * j.cin + c) * j.kh + ky) * j.kw + kx];
+    }
+    uint16_t hi, lo;
+    split16(v, j.dtype, hi, lo);
+    out[local] = part == 2 ? lo : hi;
+    return;
+  }
   if (j.stem) {
     const int n = static_cast<int>(local >> 8), k = static_cast<int>(local & 255);
     const int tap = k >> 4, ch = k & 15;
@@ -155,16 +187,6 @@ __global__ void maxpool3x3s2_kernel(const uint4* __restrict__ in, int batch, int
 }
 
 // ---------------------------------------------------------------------------------- split-precision helpers
-__device__ __forceinline__ float from16(uint16_t u, int fmt) {
-  if (fmt == FP_BF16) return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
-  return __half2float(*reinterpret_cast<__half*>(&u));
-}
-// v -> (hi, lo) with hi = round16(v), lo = round16(v - hi)
-__device__ __forceinline__ void split16(float v, int fmt, uint16_t& hi, uint16_t& lo) {
-  hi = to16(v, fmt);
-  lo = to16(v - from16(hi, fmt), fmt);
-}
-
 // K index = tap*3*cin + part*cin + c  (stem: tap*48 + part*16 + ch of the space-to-depth formulation)
 __global__ void pack_conv_weight_split_kernel(const float* __restrict__ w, int cout, int cin, int kh, int kw, int npad,
                                               int kpad, int fmt, int stem, uint16_t* __restrict__ out) {

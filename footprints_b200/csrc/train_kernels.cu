@@ -69,6 +69,12 @@ col_reduce_kernel(const uint4* __restrict__ a, int a_fmt, const uint4* __restric
       float f[8];
       unpack8(va, a_fmt, f);
       if (MODE == 0) {
+        if (y != nullptr) {            // split precision: z = hi + lo (the low halves ride in the y slot)
+          float fl[8];
+          unpack8(vy, a_fmt, fl);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] += fl[i];
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s0[i] += f[i]; s1[i] += f[i] * f[i]; }
       } else if (MODE == 1) {
@@ -95,6 +101,8 @@ col_reduce_kernel(const uint4* __restrict__ a, int a_fmt, const uint4* __restric
       if (MODE == 1) {
         if (y != nullptr) { y0 = y[i0]; y1 = y[i1]; }
         z0 = z[i0]; z1 = z[i1];
+      } else if (MODE == 0 && y != nullptr) {
+        y0 = y[i0]; y1 = y[i1];
       }
       accumulate_row(a0, y0, z0);
       accumulate_row(a1, y1, z1);
@@ -105,6 +113,8 @@ col_reduce_kernel(const uint4* __restrict__ a, int a_fmt, const uint4* __restric
       if (MODE == 1) {
         if (y != nullptr) y0 = y[i0];
         z0 = z[i0];
+      } else if (MODE == 0 && y != nullptr) {
+        y0 = y[i0];
       }
       accumulate_row(a[i0], y0, z0);
     }
@@ -198,6 +208,33 @@ __global__ void bn_apply_kernel(const uint4* __restrict__ z, const float* __rest
     f[i] = relu ? fmaxf(v, 0.f) : v;
   }
   y[idx] = pack8(f, fmt);
+}
+
+// split-precision flavour: z, residual and y are hi + lo pairs of 16-bit tensors
+__global__ void bn_apply_split_kernel(const uint4* __restrict__ zh, const uint4* __restrict__ zl,
+                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                      const uint4* __restrict__ rh, const uint4* __restrict__ rl, int relu, long long n8,
+                                      int c8, int fmt, uint4* __restrict__ yh, uint4* __restrict__ yl) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= n8) return;
+  const int cb = static_cast<int>(idx % c8) * 8;
+  float f[8], l[8], r[8], q[8];
+  unpack8(zh[idx], fmt, f);
+  unpack8(zl[idx], fmt, l);
+  if (rh != nullptr) { unpack8(rh[idx], fmt, r); unpack8(rl[idx], fmt, q); }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float v = (f[i] + l[i]) * scale[cb + i] + shift[cb + i];
+    if (rh != nullptr) v += r[i] + q[i];
+    f[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+  const uint4 hi = pack8(f, fmt);
+  float h[8];
+  unpack8(hi, fmt, h);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) l[i] = f[i] - h[i];
+  yh[idx] = hi;
+  yl[idx] = pack8(l, fmt);
 }
 
 // BatchNorm backward (training statistics), with the ReLU that follows it folded in:
@@ -614,6 +651,38 @@ extern "C" int fp_bn_stats(const void* z, long long M, int C, int dtype, const f
   bn_finalize_kernel<<<nblocks(static_cast<long long>(C) * 32, 256), 256, 0, st>>>(workspace, nblk, M, C, gamma, beta, running_mean, running_var,
                                                       momentum, eps, scale, shift, save_mean, save_invstd);
   FP_CHECK_LAUNCH("fp_bn_stats(finalize)");
+  return FP_OK;
+}
+
+extern "C" int fp_bn_stats_split(const void* z_hi, const void* z_lo, long long M, int C, int dtype, const float* gamma,
+                                 const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                 float* scale, float* shift, float* save_mean, float* save_invstd, float* workspace,
+                                 void* stream) {
+  if (!z_hi || !z_lo || !gamma || !beta || !scale || !shift || !save_mean || !save_invstd || !workspace)
+    return set_error(FP_ERR_ARG, "fp_bn_stats_split: null argument");
+  if ((C & 7) || C > 2048 || RED_THREADS % (C / 8)) return set_error(FP_ERR_ARG, "fp_bn_stats_split: unsupported C=%d", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nblk = red_blocks(M, C);
+  const int rows_per_pass = RED_THREADS / (C / 8);
+  col_reduce_kernel<0><<<nblk, RED_THREADS, rows_per_pass * 2 * C * sizeof(float), st>>>(
+      static_cast<const uint4*>(z_hi), dtype, static_cast<const uint4*>(z_lo), nullptr, dtype, nullptr, nullptr, M, C, workspace);
+  FP_CHECK_LAUNCH("fp_bn_stats_split(reduce)");
+  bn_finalize_kernel<<<nblocks(static_cast<long long>(C) * 32, 256), 256, 0, st>>>(workspace, nblk, M, C, gamma, beta, running_mean, running_var,
+                                                      momentum, eps, scale, shift, save_mean, save_invstd);
+  FP_CHECK_LAUNCH("fp_bn_stats_split(finalize)");
+  return FP_OK;
+}
+
+extern "C" int fp_bn_apply_split(const void* z_hi, const void* z_lo, const float* scale, const float* shift,
+                                 const void* res_hi, const void* res_lo, int relu, long long M, int C, int dtype, void* y_hi,
+                                 void* y_lo, void* stream) {
+  if (!z_hi || !z_lo || !scale || !shift || !y_hi || !y_lo || (C & 7) || ((res_hi == nullptr) != (res_lo == nullptr)))
+    return set_error(FP_ERR_ARG, "fp_bn_apply_split: bad argument");
+  const long long n8 = M * (C / 8);
+  bn_apply_split_kernel<<<nblocks(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(z_hi), static_cast<const uint4*>(z_lo), scale, shift, static_cast<const uint4*>(res_hi),
+      static_cast<const uint4*>(res_lo), relu, n8, C / 8, dtype, static_cast<uint4*>(y_hi), static_cast<uint4*>(y_lo));
+  FP_CHECK_LAUNCH("fp_bn_apply_split");
   return FP_OK;
 }
 

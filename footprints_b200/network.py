@@ -167,7 +167,7 @@ class FootprintNetwork(nn.Module):
 
     def __init__(self, pretrained=True, blocks=(3, 4, 6, 3), compute_dtype='fp16', precise=False):
         super().__init__()
-        self.precise = precise          # eval: split-precision layers upstream of the low-resolution mask heads (engine.py)
+        self.precise = precise          # split-precision layers upstream of the low-resolution mask heads (engine.py), eval and train forward
         self.encoder = ResnetEncoder(pretrained=pretrained, blocks=blocks)
         self.mask_decoder = SkipDecoder(apply_sigmoid=False)
         self.depth_decoder = SkipDecoder(apply_sigmoid=True)
@@ -184,7 +184,7 @@ class FootprintNetwork(nn.Module):
     def train_engine(self):
         if self._train_engine is None:
             from .train_engine import TrainEngine
-            self._train_engine = TrainEngine(self, self.train_dtype)
+            self._train_engine = TrainEngine(self, self.train_dtype, self.precise)
         return self._train_engine
 
     def forward(self, input_image):

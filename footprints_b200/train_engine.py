@@ -31,15 +31,15 @@ from . import _lib
 import math
 
 from ._lib import FP_ACT_ELU, FP_ACT_NONE, FP_ACT_RELU, FP_BF16, FP_F16, FP_PAD_ZERO, FpConvDesc
-from .engine import SCALES, Engine, _bn_tile, _ptr
+from .engine import PRECISE_PREFIXES, SCALES, Engine, _bn_tile, _ptr
 
 _RAW = object()   # sentinel: run the conv with no scale/shift (NULL pointers)
 
 
 class TrainEngine(Engine):
 
-    def __init__(self, net, compute_dtype='fp16'):
-        super().__init__(net, compute_dtype)
+    def __init__(self, net, compute_dtype='fp16', precise=False):
+        super().__init__(net, compute_dtype, precise)
         self.gfmt = self.fmt                 # gradients share the activations' 16-bit type (see the module docstring)
         self.gdtype = self.tdtype
         self.loss_scale = None               # None: 2^k ~ 32 * 4*B*H*W for fp16 gradients, 1 for bf16; or a fixed float
@@ -99,10 +99,24 @@ class TrainEngine(Engine):
             if L.stem:
                 jobs.append(_lib.FpPackJob(w.data_ptr(), L.w_packed.data_ptr(), L.cout, 3, 7, 7, 16, L.npad, 256, self.fmt, 0, 1, first))
                 first += L.npad * 256
+                if self.precise:
+                    if getattr(L, 'w_packed3', None) is None:
+                        L.kpad3 = 768
+                        L.w_packed3 = torch.empty((L.npad, 768), dtype=self.tdtype, device=dev)
+                    jobs.append(_lib.FpPackJob(w.data_ptr(), L.w_packed3.data_ptr(), L.cout, 3, 7, 7, 16, L.npad, 768, self.fmt, 2, 1, first))
+                    first += L.npad * 768
                 continue
             jobs.append(_lib.FpPackJob(w.data_ptr(), L.w_packed.data_ptr(), L.cout, cin, L.k, L.k, cin, L.npad, L.kpad,
                                        self.fmt, 0, 0, first))
             first += L.npad * L.kpad
+            if self.precise and L.name.startswith(PRECISE_PREFIXES):       # [Whi | Whi | Wlo] per tap (flip = 2)
+                if getattr(L, 'w_packed3', None) is None:
+                    L.kpad3 = 768 if L.stem else (3 * L.k * L.k * cin + 63) // 64 * 64
+                    L.w_packed3 = torch.empty((L.npad, L.kpad3), dtype=self.tdtype, device=dev)
+                jobs.append(_lib.FpPackJob(w.data_ptr(), L.w_packed3.data_ptr(), L.cout, 3 if L.stem else cin,
+                                           7 if L.stem else L.k, 7 if L.stem else L.k, 16 if L.stem else cin, L.npad,
+                                           L.kpad3, self.fmt, 2, 1 if L.stem else 0, first))
+                first += L.npad * L.kpad3
             if L.is_head:
                 continue            # the heads' data gradient runs on the CUDA-core kernel (fp32 parameters)
             # data-gradient operand: rows = cin, K = taps * cout_pad, filter rotated by 180 degrees
@@ -184,6 +198,8 @@ class TrainEngine(Engine):
         def new(shape, dtype=None):
             return torch.empty(shape, dtype=dtype or self.tdtype, device=dev)
 
+        if self.precise:
+            return self._forward_train_precise(image, save, stream, sv)
         s2d = new((b, h // 2, w // 2, 16))
         _lib.check(lib.fp_stem_prep(_ptr(image), b, h, w, self.fmt, _ptr(s2d), stream))
         f0 = self._conv_bn(self.layers['stem'], s2d, None, True, stream, sv)
@@ -254,6 +270,138 @@ class TrainEngine(Engine):
         # torchvision BatchNorm2d bookkeeping (num_batches_tracked += 1 per BN per forward): one multi-tensor launch
         torch._foreach_add_([L.bn.num_batches_tracked for L in self.layers.values() if L.bn is not None], 1)
         self.net._weights_epoch = getattr(self.net, '_weights_epoch', 0) + 1      # running statistics changed (raw pointers)
+        return outputs, (sv if save else None)
+
+    # ------------------------------------------------------------------------------ precise (split-precision) forward
+    def _conv_bn_split(self, L, src, residual, relu, stream, saved):
+        """_conv_bn on hi + lo pairs: split-precision convolution, batch statistics over hi + lo, split BatchNorm apply.
+        The backward reads the HIGH halves only (they are what the fast path stores), so they are what is saved."""
+        b, h, w, _ = src[0].shape
+        ho, wo = (h // L.stride, w // L.stride) if not L.stem else (h, w)
+        dev = src[0].device
+        z = tuple(torch.empty((b, ho, wo, L.cout), dtype=self.tdtype, device=dev) for _ in range(2))
+        s0, s1, a0 = L.scale, L.shift, L.act
+        L.scale, L.shift, L.act = None, None, FP_ACT_NONE
+        try:
+            self._conv_split(L, src, None, z, None, stream)
+        finally:
+            L.scale, L.shift, L.act = s0, s1, a0
+        stv = torch.empty((4, L.cout), dtype=torch.float32, device=dev)
+        st = {'scale': stv[0], 'shift': stv[1], 'mean': stv[2], 'invstd': stv[3]}
+        bn = L.bn
+        M = b * ho * wo
+        _lib.check(self.lib.fp_bn_stats_split(_ptr(z[0]), _ptr(z[1]), M, L.cout, self.fmt, _ptr(bn.weight.detach()),
+                                              _ptr(bn.bias.detach()), _ptr(bn.running_mean), _ptr(bn.running_var),
+                                              float(bn.momentum), float(bn.eps), _ptr(st['scale']), _ptr(st['shift']),
+                                              _ptr(st['mean']), _ptr(st['invstd']), _ptr(self._reduce_ws()), stream))
+        y = (torch.empty_like(z[0]), torch.empty_like(z[0]))
+        _lib.check(self.lib.fp_bn_apply_split(_ptr(z[0]), _ptr(z[1]), _ptr(st['scale']), _ptr(st['shift']),
+                                              _ptr(residual[0]) if residual is not None else None,
+                                              _ptr(residual[1]) if residual is not None else None, 1 if relu else 0, M,
+                                              L.cout, self.fmt, _ptr(y[0]), _ptr(y[1]), stream))
+        self.launches += 3
+        saved[L.name] = (src[0], z[0], y[0])
+        saved['bn'][L.name] = st
+        return y
+
+    def _forward_train_precise(self, image, save, stream, sv):
+        """forward_train with the PRECISE_PREFIXES layers in split precision (same saved-state layout: the backward is
+        unchanged and reads the high halves)."""
+        lib = self.lib
+        b, _, h, w = image.shape
+        dev = image.device
+
+        def new(shape, dtype=None):
+            return torch.empty(shape, dtype=dtype or self.tdtype, device=dev)
+
+        def pair(shape):
+            return new(shape), new(shape)
+
+        s2d = pair((b, h // 2, w // 2, 16))
+        _lib.check(lib.fp_stem_prep_split(_ptr(image), b, h, w, self.fmt, _ptr(s2d[0]), _ptr(s2d[1]), stream))
+        f0 = self._conv_bn_split(self.layers['stem'], s2d, None, True, stream, sv)
+        x = pair((b, h // 4, w // 4, 64))
+        _lib.check(lib.fp_maxpool3x3s2_split(_ptr(f0[0]), _ptr(f0[1]), b, h // 2, w // 2, 64, self.fmt, _ptr(x[0]), _ptr(x[1]),
+                                             stream))
+        sv['pool'] = x[0]
+        feats = [f0]
+        last_li = 0
+        for li, c1, ds, c2 in self.enc_blocks:
+            if li != last_li:
+                feats.append(x)
+                last_li = li
+            t1 = self._conv_bn_split(c1, x, None, True, stream, sv)
+            idt = x
+            if ds is not None:
+                idt = self._conv_bn_split(ds, x, None, False, stream, sv)
+            x = self._conv_bn_split(c2, t1, idt, True, stream, sv)
+        feats.append(x)
+        sv['feats'] = [f[0] for f in feats]
+
+        heads = {}
+        for dname in ('mask', 'depth'):
+            d = self.dec[dname]
+            x = feats[4] if dname == 'mask' else feats[4][0]
+            for bi in range(1, 5):
+                skip = feats[4 - bi]
+                if dname == 'mask' and bi <= 2:
+                    hh, ww = x[0].shape[1], x[0].shape[2]
+                    co = d[f'b{bi}.pre1'].cout
+                    t = pair((b, hh, ww, co))
+                    self._conv_split(d[f'b{bi}.pre1'], x, None, t, None, stream)
+                    sv[d[f'b{bi}.pre1'].name] = (x[0], None, t[0])
+                    t2 = pair((b, hh, ww, co))
+                    self._conv_split(d[f'b{bi}.pre2'], t, None, t2, None, stream)
+                    sv[d[f'b{bi}.pre2'].name] = (t[0], None, t2[0])
+                    t3 = pair((b, 2 * hh, 2 * ww, co))
+                    self._conv_split(d[f'b{bi}.post1'], t2, skip, t3, None, stream)
+                    sv[d[f'b{bi}.post1'].name] = (t2[0], skip[0], t3[0])
+                    x = pair((b, 2 * hh, 2 * ww, co))
+                    self._conv_split(d[f'b{bi}.post2'], t3, None, x, None, stream)
+                    sv[d[f'b{bi}.post2'].name] = (t3[0], None, x[0])
+                    if bi == 2:
+                        hd = new((b, 2 * hh, 2 * ww, 2), torch.float32)
+                        self._conv_split(d['head1'], x, None, (hd, None), None, stream)
+                        sv[d['head1'].name] = (x[0], None, hd)
+                        heads[(dname, 1)] = hd
+                    continue
+                if isinstance(x, tuple):
+                    x = x[0]                  # leaving the precise set: the high halves are the tensor
+                hh, ww = x.shape[1], x.shape[2]
+                co = d[f'b{bi}.pre1'].cout
+                t = new((b, hh, ww, co))
+                self._conv(d[f'b{bi}.pre1'], x, None, t, None, stream)
+                sv[d[f'b{bi}.pre1'].name] = (x, None, t)
+                t2 = new((b, hh, ww, co))
+                self._conv(d[f'b{bi}.pre2'], t, None, t2, None, stream)
+                sv[d[f'b{bi}.pre2'].name] = (t, None, t2)
+                t3 = new((b, 2 * hh, 2 * ww, co))
+                self._conv(d[f'b{bi}.post1'], t2, skip[0], t3, None, stream)
+                sv[d[f'b{bi}.post1'].name] = (t2, skip[0], t3)
+                x = new((b, 2 * hh, 2 * ww, co))
+                self._conv(d[f'b{bi}.post2'], t3, None, x, None, stream)
+                sv[d[f'b{bi}.post2'].name] = (t3, None, x)
+                if bi >= 2:
+                    hd = new((b, 2 * hh, 2 * ww, 2), torch.float32)
+                    self._head(d[f'head{bi - 1}'], x, hd, stream)
+                    sv[d[f'head{bi - 1}'].name] = (x, None, hd)
+                    heads[(dname, bi - 1)] = hd
+            hh, ww = x.shape[1], x.shape[2]
+            t = new((b, 2 * hh, 2 * ww, 32))
+            self._conv(d['o4.c1'], x, None, t, None, stream)
+            sv[d['o4.c1'].name] = (x, None, t)
+            t2 = new((b, 2 * hh, 2 * ww, 32))
+            self._conv(d['o4.c2'], t, None, t2, None, stream)
+            sv[d['o4.c2'].name] = (t, None, t2)
+            hd = new((b, 2 * hh, 2 * ww, 2), torch.float32)
+            self._head(d['head4'], t2, hd, stream)
+            sv[d['head4'].name] = (t2, None, hd)
+            heads[(dname, 4)] = hd
+        outputs = self._assemble(heads, b, h, w, dev, stream)
+        sv['s2d'] = s2d[0]
+        sv['shape'] = (b, h, w)
+        torch._foreach_add_([L.bn.num_batches_tracked for L in self.layers.values() if L.bn is not None], 1)
+        self.net._weights_epoch = getattr(self.net, '_weights_epoch', 0) + 1
         return outputs, (sv if save else None)
 
     # ------------------------------------------------------------------------------ backward pieces

@@ -103,6 +103,13 @@ int fp_stem_prep_split(const float* image_nchw, int batch, int h, int w, int dty
 int fp_maxpool3x3s2_split(const void* in_hi, const void* in_lo, int batch, int h, int w, int c, int dtype, void* out_hi,
                           void* out_lo, void* stream);
 
+/* Train-mode BatchNorm of fp_bn_stats / fp_bn_apply on hi + lo pairs (precise mode's training forward). */
+int fp_bn_stats_split(const void* z_hi, const void* z_lo, long long M, int C, int dtype, const float* gamma,
+                      const float* beta, float* running_mean, float* running_var, float momentum, float eps, float* scale,
+                      float* shift, float* save_mean, float* save_invstd, float* workspace, void* stream);
+int fp_bn_apply_split(const void* z_hi, const void* z_lo, const float* scale, const float* shift, const void* res_hi,
+                      const void* res_lo, int relu, long long M, int C, int dtype, void* y_hi, void* y_lo, void* stream);
+
 /* OIHW fp32 -> packed [npad][kpad] 16-bit, K index = (ky*kw + kx)*cpad + c (tap-major, channel-minor),
  * zero padded; cpad >= the channel-minor extent (cin, or cout when flipped) is the channel count of the
  * tensor the kernel will gather (a power of two >= 8 together with a concat partner).  flip=1 packs the
@@ -115,7 +122,8 @@ int fp_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw, 
 /* All weight operands of a network in ONE launch (training re-packs ~142 of them every step; §8 f1: this launch follows
  * fp_adam_step in the optimiser pass).  jobs_dev: device array sorted by `first`; job i produces packed elements
  * [first_i, first_{i+1}) of the concatenated output index space (`total` = end of the last job) with the semantics of
- * fp_pack_conv_weight (stem = 0) or fp_pack_stem_weight (stem = 1: kpad is 256, cpad / kh / kw / flip unused). */
+ * fp_pack_conv_weight (stem = 0) or fp_pack_stem_weight (stem = 1: kpad is 256, cpad / kh / kw / flip unused);
+ * flip = 2 selects the split-precision layouts of fp_pack_conv_weight_split / fp_pack_stem_weight_split. */
 typedef struct FpPackJob {
   const float* w;     /* OIHW fp32 parameter                      */
   void* out;          /* packed [npad][kpad] 16-bit               */

@@ -17,3 +17,7 @@ echo "== launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python scripts/one_step.py > gpurun_out/${TAG}_one_step.log 2>&1; python scripts/launch_summary.py gpurun_out/${TAG}_launches.csv 2 > gpurun_out/${TAG}_launch_summary.md; head -45 gpurun_out/${TAG}_launch_summary.md
 echo "== bench"
 timeout 400 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; cut -c1-400 gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
+echo "== bench precise / infer"
+timeout 400 python bench.py --precise --no-cpu-baseline > gpurun_out/${TAG}_bench_precise.json 2> gpurun_out/${TAG}_bench_precise.err; cut -c1-260 gpurun_out/${TAG}_bench_precise.json; tail -2 gpurun_out/${TAG}_bench_precise.err
+timeout 300 python bench.py --mode infer --no-cpu-baseline > gpurun_out/${TAG}_bench_infer.json 2> gpurun_out/${TAG}_bench_infer.err; cut -c1-260 gpurun_out/${TAG}_bench_infer.json
+timeout 300 python bench.py --mode infer --precise --no-cpu-baseline > gpurun_out/${TAG}_bench_infer_precise.json 2> gpurun_out/${TAG}_bench_infer_precise.err; cut -c1-260 gpurun_out/${TAG}_bench_infer_precise.json; tail -2 gpurun_out/${TAG}_bench_infer_precise.err

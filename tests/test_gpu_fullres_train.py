@@ -131,3 +131,44 @@ def test_eval_forward_random_init_weights(shape):
         mag = ref[k][:, :2].abs().max().item()
         print(f'random-init eval {shape} scale {k}: max abs err {err:.3e} (logit range {mag:.2f}, bar {TOL["fp16"][k]:.0e})')
         assert err <= TOL['fp16'][k], (k, err)
+
+
+def test_precise_train_step_meets_1e_3_on_every_scale():
+    """``FootprintNetwork(precise=True).train()``: train-mode forward (batch-statistics BatchNorm) with the layers
+    upstream of the low-resolution mask heads in split precision -- all four scales within 1e-3 of the reference's own
+    train-mode outputs (fixture, 1x192x640) and of the oracle at 4x192x640; the backward (unchanged, high halves) still
+    matches the reference's gradient norms."""
+    g = np.load(os.path.join(GOLD, 'ref_resnet34_b1_192x640.npz'))
+    net = FootprintNetwork(pretrained=False, precise=True)
+    net.load_state_dict(synthetic_state_dict('resnet34', 0))
+    net = net.cuda().train()
+    data = synthetic_batch(1, 192, 640, 1)
+    out = net(data['image'].cuda())
+    for k in O.SCALES:
+        idx = torch.from_numpy(g[f'train/{k}/idx']).long()
+        err = np.abs(out[k].detach().cpu().flatten()[idx].numpy() - g[f'train/{k}/val']).max()
+        print(f'precise train fwd 1x192x640 scale {k}: max abs err vs reference fixture {err:.3e} (bar 1e-03)')
+        assert err <= 1e-3, (k, err)
+    targets = {k: v.cuda() for k, v in data.items() if k != 'image'}
+    losses = LossManager((0.1, 100.0), 0.25, side_outputs=False)(out, targets)
+    assert abs(losses['loss'].item() - float(g['loss/loss'])) <= 2e-3 * float(g['loss/loss'])
+    net.zero_grad()
+    losses['loss'].backward()
+    named = dict(net.named_parameters())
+    for name, ref_norm in zip(g['grad_names'], g['grad_norms']):
+        n = named[str(name)].grad.double().norm().item()
+        assert abs(n - ref_norm) <= 0.1 * ref_norm + 1e-12, (str(name), n, ref_norm)
+    sd = net.state_dict()
+    for k in ('encoder.layer0.1.running_mean', 'encoder.layer0.1.running_var', 'encoder.layer4.1.bn2.running_var'):
+        assert torch.allclose(sd[k].cpu(), torch.from_numpy(g[f'bnstat/{k}']), rtol=2e-3, atol=2e-3), k
+    # batch 4 against the oracle
+    sd0 = synthetic_state_dict('resnet34', 0)
+    net.load_state_dict(sd0)
+    data = synthetic_batch(4, 192, 640, 5)
+    with torch.no_grad():
+        out = net(data['image'].cuda())
+    ref = O.network_forward(sd0, data['image'], 'resnet34', training=True, new_stats={})
+    for k in O.SCALES:
+        err = (out[k].cpu() - ref[k]).abs().max().item()
+        print(f'precise train fwd 4x192x640 scale {k}: max abs err vs oracle {err:.3e} (bar 1e-03)')
+        assert err <= 1e-3, (k, err)
