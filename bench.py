@@ -34,12 +34,20 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='images per GPU')
+    ap.add_argument('--hw', default='192x640', help='input height x width (KITTI 192x640; Matterport 512x640 with --batch 16)')
+    ap.add_argument('--cpu-batch', type=int, default=4, help='fixed batch of the CPU reference arm / cpu_baseline sample')
     ap.add_argument('--arch', default='resnet34', choices=['resnet34', 'resnet18'])
     ap.add_argument('--mode', default='train', choices=['train', 'infer'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--precise', action='store_true', help='split-precision layers upstream of the low-resolution mask heads (all four output scales within 1e-3 of the fp32 reference)')
+    ap.add_argument('--no-precise', action='store_true', help='skip the extra precise-mode measurement')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying the CUDA graph of the step')
-    return ap.parse_args()
+    args = ap.parse_args()
+    global H, W, METRIC
+    H, W = (int(v) for v in args.hw.lower().split('x'))
+    if (H, W, args.batch) != (192, 640, 64):
+        METRIC = f'images/sec fwd+bwd {H}x{W} bs={args.batch}/GPU'
+    return args
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -98,30 +106,63 @@ def usable_cores():
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
+def _reference_modules():
+    """The UNMODIFIED reference (baseline/_ref placed by scripts/install_reference.sh; SURVEY §8c shims in-process), or None."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        import reference_shims
+        if reference_shims.import_reference() is None:
+            return None
+        import footprints.network as fn
+        from footprints.training.losses import LossManager
+        return fn, LossManager
+    except Exception:
+        return None
+
+
 def cpu_train_steps(arch, batch, steps, warmup, threads):
-    """The reference algorithm's training step on host cores: oracle forward (train-mode BN) + LossManager
-    restatement + autograd backward + torch.optim.Adam — a port of footprints/training/train.py:153-156."""
+    """The reference's training step on host cores (footprints/training/train.py:153-156,224-225): forward in train mode,
+    LossManager, backward, Adam.  Runs the reference's OWN modules when the unmodified package is importable
+    (kind 'reference'), else the oracle port of the same arithmetic (kind 'port').  Returns (seconds per step, kind)."""
     import torch
     from footprints_b200.synthetic import synthetic_batch, synthetic_state_dict
-    from oracle import footprints_oracle as O
     torch.set_num_threads(threads)
-    sd = synthetic_state_dict(arch, 0, trained_like=False)
-    params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(('running_mean', 'running_var'))
-                  else v.clone()) for k, v in sd.items()}
-    used = [v for k, v in params.items() if v.is_floating_point() and v.requires_grad]
-    opt = torch.optim.Adam(used, lr=1e-4)
     data = synthetic_batch(batch, H, W, 1)
+    ref = _reference_modules() if arch == 'resnet34' else None
+    if ref is not None:
+        fn, LossManager = ref
+        torch.manual_seed(0)
+        net = fn.FootprintNetwork(pretrained=False).train()
+        lm = LossManager((0.1, 100.0), 0.25)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+        targets = {k: v for k, v in data.items() if k != 'image'}
+
+        def one():
+            losses = lm(net(data['image']), targets)
+            net.zero_grad()
+            losses['loss'].backward()
+            opt.step()
+        kind = 'reference'
+    else:
+        from oracle import footprints_oracle as O
+        sd = synthetic_state_dict(arch, 0, trained_like=False)
+        params = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(('running_mean', 'running_var'))
+                      else v.clone()) for k, v in sd.items()}
+        opt = torch.optim.Adam([v for v in params.values() if v.is_floating_point() and v.requires_grad], lr=1e-4)
+
+        def one():
+            losses = O.loss_forward(O.network_forward(params, data['image'], arch, True, {}), data)
+            opt.zero_grad(set_to_none=True)
+            losses['loss'].backward()
+            opt.step()
+        kind = 'port'
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        outs = O.network_forward(params, data['image'], arch, True, {})
-        losses = O.loss_forward(outs, data)
-        opt.zero_grad(set_to_none=True)
-        losses['loss'].backward()
-        opt.step()
+        one()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return sum(times) / len(times)
+    return sum(times) / len(times), kind
 
 
 def run_reference(args):
@@ -130,19 +171,19 @@ def run_reference(args):
     if rank != 0:
         return
     threads = usable_cores()
-    # bounded sample: pick the per-step batch so that the whole run stays within a few minutes
-    t_probe = cpu_train_steps(args.arch, 1, 1, 0, threads)
-    budget = 150.0
-    per_step = max(1, min(8, int(budget / max(1e-3, t_probe * (args.steps + args.warmup)))))
-    t = cpu_train_steps(args.arch, per_step, args.steps, min(args.warmup, 1), threads)
+    # bounded sample with a FIXED batch (the same at every N, so the driver's ratio has a stable denominator)
+    per_step = args.cpu_batch
+    steps = max(1, min(args.steps, 4))
+    t, kind = cpu_train_steps(args.arch, per_step, steps, 1, threads)
     value = per_step / t
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus,
-            'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': t * 1e3, 'higher_is_better': True,
+            'steps': steps, 'warmup': 1, 'ms_per_step': t * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'training step (fwd train-BN + loss + bwd + Adam), {args.arch} encoder + 2 skip decoders, '
                                    f'{H}x{W}; CPU sample of {per_step} image(s)/step', 'arch': args.arch},
-            'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
-                             'sample': f'{args.steps} steps of batch {per_step} at {H}x{W}, torch {torch.__version__} CPU'},
+            'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': threads, 'kind': kind,
+                             'sample': f'{steps} steps of batch {per_step} at {H}x{W}, torch {torch.__version__} CPU, '
+                                       + ('the unmodified reference modules (baseline/_ref)' if kind == 'reference' else 'oracle port')},
             'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -293,8 +334,8 @@ def main():
         if top is not None:
             t_top = top[3].elapsed_time(top[4])
             top_launch = {'layer': top[1], 'kind': top[0], 'ms': t_top, 'tflops': top[2] / (t_top * 1e-3) / 1e12}
-            try:
-                tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+            try:        # dram__bytes_read.sum + dram__bytes_write.sum of this launch from this round's `ncu --set full`
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))     # capture; null when absent
                 key = top[1].split('.', 1)[-1] + '/' + top[0]          # 'mask.o4.c1' -> 'o4.c1/fwd'
                 if B == 64 and (H, W) == (192, 640) and key in tj['bytes_per_launch']:
                     traffic = tj['bytes_per_launch'][key]
@@ -325,13 +366,60 @@ def main():
         except Exception as exc:               # never lose the bench line over the secondary view
             roofline['decoder_fwd_hbm'] = {'error': repr(exc)}
 
+    # top-level copies of the per-class roofline views (the driver's parser keeps top-level keys)
+    extra = {}
+    if rank == 0 and roofline is not None:
+        def view(rows, label):
+            t = sum(x[3].elapsed_time(x[4]) for x in rows)
+            fl = sum(x[2] for x in rows)
+            if t <= 0:
+                return None
+            return {'bound': 'tensor', 'kernel': label, 'achieved': fl / (t * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
+                    'frac': fl / (t * 1e-3) / 1e12 / peak, 'ms_per_step': t, 'launches': len(rows),
+                    'algorithmic_gflop_per_step': fl / 1e9}
+        extra['roofline_wgrad'] = view([x for x in prof if x[0] == 'wgrad'], 'weight-gradient kernels (conv_wgrad_roll / _strip / general + reduce)')
+        extra['roofline_encoder_fwd'] = view([x for x in prof if x[0] == 'fwd' and x[1].startswith(('stem', 'enc'))],
+                                             'encoder forward convolutions (stem + 36 BasicBlock convolutions)')
+        extra['roofline_decoder_fwd'] = view([x for x in prof if x[0] == 'fwd' and x[1].startswith(('mask', 'depth'))],
+                                             'decoder forward convolutions (tensor-pipe view)')
+        extra['roofline_decoder_hbm'] = roofline.get('decoder_fwd_hbm')
+        conv_ms = sum(v[0] for v in agg.values())
+        extra['step_breakdown'] = {'conv_kernels_ms': conv_ms, 'other_kernels_ms': max(0.0, ms_per_step - conv_ms),
+                                   'note': 'conv = CUDA-event time of every fwd/dgrad/wgrad launch of the instrumented step'}
+        flops_step = sum(v[1] for v in agg.values())
+        extra['roofline_whole_step'] = {'bound': 'tensor', 'achieved': flops_step / (ms_per_step * 1e-3) / 1e12, 'peak': peak,
+                                        'unit': 'TFLOP/s', 'frac': flops_step / (ms_per_step * 1e-3) / 1e12 / peak}
+
+    # precise mode (split precision upstream of the low-resolution mask heads: all four output scales within 1e-3 of the
+    # fp32 reference) measured beside the default single-pass mode, same workload
+    if rank == 0 and world == 1 and not args.precise and not args.no_precise:
+        try:
+            del step_resident
+            torch.cuda.empty_cache()
+            net2 = FootprintNetwork(pretrained=False, blocks=blocks, precise=True).cuda()
+            if args.mode == 'train':
+                net2.train()
+                tr2 = Trainer(net2, lr=1e-4).enable_cuda_graph()
+                fn2 = lambda: tr2.step(dev['image'], {k: dev[k] for k in tkeys})
+            else:
+                net2.eval()
+                fn2 = lambda: net2(dev['image'])['1/1']
+            for _ in range(3):
+                fn2()
+            ms2 = timed(fn2, max(3, args.steps // 2)) / max(3, args.steps // 2)
+            extra['precise'] = {'value': B / (ms2 * 1e-3), 'unit': 'images/s', 'ms_per_step': ms2,
+                                'note': 'FootprintNetwork(precise=True): every output scale within 1e-3 max-abs of the fp32 reference (tests)'}
+        except Exception as exc:
+            extra['precise'] = {'error': repr(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.mode == 'train':
         threads = usable_cores()
-        bs = 2
-        t = cpu_train_steps(args.arch, bs, 2, 1, threads)
-        cpu = {'value': bs / t, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
-               'sample': f'2 training steps of batch {bs} at {H}x{W} (oracle port of the reference PyTorch path, fp32)'}
+        bs = args.cpu_batch
+        t, kind = cpu_train_steps(args.arch, bs, 2, 1, threads)
+        cpu = {'value': bs / t, 'unit': 'images/s', 'cores': threads, 'kind': kind,
+               'sample': f'2 training steps of batch {bs} at {H}x{W}, fp32, '
+                         + ('the unmodified reference modules (baseline/_ref)' if kind == 'reference' else 'oracle port of the reference path')}
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
@@ -346,6 +434,9 @@ def main():
                 'e2e': {'value': e2e_value, 'unit': 'images/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': d2h},
                 'gpu_launches': launches, 'clocks': clocks}
+        line['config']['precise'] = bool(args.precise)
+        line['config']['cuda_graph'] = bool(args.mode == 'train' and not args.no_graph)
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -10,6 +10,7 @@ Layout: activations are NHWC 16-bit (fp16 or bf16); weights are packed K-major
 per-channel fp32 scale/shift applied in the convolution epilogue.
 """
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
@@ -77,6 +78,7 @@ class Engine:
         self._weight_key = None
         self._bufs = {}
         self.head_tensor_cores = True
+        self.nvtx = os.environ.get('FP_NVTX', '0') == '1'      # per-launch NVTX ranges (profiling)
         self.launches = 0           # kernels launched through the C ABI (bench.py reports them)
         self.profile = None         # when a list: (kind, layer, flops, start_event, end_event, algorithmic_bytes) per conv launch
         self._prof_open = None
@@ -85,6 +87,8 @@ class Engine:
     def _prof(self, kind, L, m_pixels, abytes=0):
         """abytes: algorithmic HBM bytes of the launch (unique input elements once, pre-upsample / pre-pad,
         the concatenated skip included, + outputs once + weights once), 0 when the caller does not track it."""
+        if self.nvtx:                   # NVTX range "<kind>:<layer>" around the launch (ncu --nvtx --nvtx-include ...)
+            torch.cuda.nvtx.range_push(f'{kind}:{L.name}')
         if self.profile is None:
             return
         k_real = 147 if L.stem else L.k * L.k * (L.cin0 + L.cin1)
@@ -95,6 +99,8 @@ class Engine:
         self._prof_open = (kind, L.name, flops, e0, e1, abytes)
 
     def _prof_end(self):
+        if self.nvtx:
+            torch.cuda.nvtx.range_pop()
         if self._prof_open is not None:
             self._prof_open[4].record()
             self.profile.append(self._prof_open)

@@ -21,3 +21,7 @@ echo "== bench precise / infer"
 timeout 400 python bench.py --precise --no-cpu-baseline > gpurun_out/${TAG}_bench_precise.json 2> gpurun_out/${TAG}_bench_precise.err; cut -c1-260 gpurun_out/${TAG}_bench_precise.json; tail -2 gpurun_out/${TAG}_bench_precise.err
 timeout 300 python bench.py --mode infer --no-cpu-baseline > gpurun_out/${TAG}_bench_infer.json 2> gpurun_out/${TAG}_bench_infer.err; cut -c1-260 gpurun_out/${TAG}_bench_infer.json
 timeout 300 python bench.py --mode infer --precise --no-cpu-baseline > gpurun_out/${TAG}_bench_infer_precise.json 2> gpurun_out/${TAG}_bench_infer_precise.err; cut -c1-260 gpurun_out/${TAG}_bench_infer_precise.json; tail -2 gpurun_out/${TAG}_bench_infer_precise.err
+echo "== bench 512x640 bs16"
+timeout 300 python bench.py --hw 512x640 --batch 16 --no-cpu-baseline --no-precise > gpurun_out/${TAG}_bench_512x640_bs16.json 2> gpurun_out/${TAG}_bench_512.err; cut -c1-260 gpurun_out/${TAG}_bench_512x640_bs16.json; tail -2 gpurun_out/${TAG}_bench_512.err
+echo "== reference arm"
+timeout 600 python bench.py --impl reference --steps 2 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_ref.err; cut -c1-400 gpurun_out/${TAG}_bench_reference_arm.json; tail -2 gpurun_out/${TAG}_ref.err

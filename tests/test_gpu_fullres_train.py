@@ -172,3 +172,34 @@ def test_precise_train_step_meets_1e_3_on_every_scale():
         err = (out[k].cpu() - ref[k]).abs().max().item()
         print(f'precise train fwd 4x192x640 scale {k}: max abs err vs oracle {err:.3e} (bar 1e-03)')
         assert err <= 1e-3, (k, err)
+
+
+def test_train_step_matterport_shape_512x640():
+    """BASELINE.json configs[4] geometry (Matterport 512x640; ResNet-18 encoder variant -- the ResNet-50 one is not
+    expressible with the reference decoder): one training step at 2x512x640 against the oracle."""
+    sd = synthetic_state_dict('resnet18', 0)
+    data = synthetic_batch(2, 512, 640, 8)
+    net = FootprintNetwork(pretrained=False, blocks=(2, 2, 2, 2))
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    tol = TRAIN_TOL[net.train_dtype]
+    ref_out, ref_losses, g32, _ = O.train_step_reference(sd, data, 'resnet18')
+    out = net(data['image'].cuda())
+    for k in O.SCALES:
+        assert out[k].shape == (2, 4, 512, 640)
+        err = (out[k].detach().cpu() - ref_out[k].detach()).abs().max().item()
+        print(f'train fwd 2x512x640 resnet18 scale {k}: max abs err vs oracle {err:.3e} (bar {tol[k]:.0e})')
+        assert err <= tol[k], (k, err)
+    targets = {k: v.cuda() for k, v in data.items() if k != 'image'}
+    losses = LossManager((0.1, 100.0), 0.25, side_outputs=False)(out, targets)
+    assert abs(losses['loss'].item() - ref_losses['loss'].item()) <= 5e-3 * ref_losses['loss'].item()
+    net.zero_grad()
+    losses['loss'].backward()
+    named = dict(net.named_parameters())
+    for name, gref in g32.items():
+        a = named[name].grad.detach().float().cpu()
+        assert torch.isfinite(a).all(), name
+        ratio = (a.double().norm() / (gref.double().norm() + 1e-300)).item()
+        assert 0.9 <= ratio <= 1.1, (name, ratio)
+        if name.startswith(('mask_decoder', 'depth_decoder')):
+            assert _cos(a, gref) >= 0.98, (name, _cos(a, gref))
