@@ -309,8 +309,13 @@ def main():
     # every rank runs the instrumented step (it contains the gradient all-reduce); only rank 0 records events
     if rank == 0:
         eng.profile = []
+    overlap = getattr(eng, 'overlap_wgrad', False)
+    if hasattr(eng, 'overlap_wgrad'):
+        eng.overlap_wgrad = False          # per-launch CUDA-event times need the launches serialised on one stream
     step_resident()
     torch.cuda.synchronize()
+    if hasattr(eng, 'overlap_wgrad'):
+        eng.overlap_wgrad = overlap
     if rank == 0:
         prof, eng.profile = eng.profile, None
         agg = {}

@@ -62,7 +62,7 @@ struct IgemmCfg {
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator stages, power of two
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) +
-                                    (2 * STAGES + 4) * 8 + 16 + 2 * BN * 4 + 2 * BM * 16 + KTAB_ENTRIES * 4;
+                                    (2 * STAGES + 4) * 8 + 32 + 2 * BN * 4 + 2 * BM * 16 + KTAB_ENTRIES * 4;
 };
 
 struct IgemmParams {
@@ -134,14 +134,24 @@ __device__ __forceinline__ void epilogue_store16(const IgemmParams& p, const uin
   if (n0 >= p.N) return;
   if (p.out_f32 && p.N - n0 == 2 && p.out_ld == 2 && p.residual == nullptr) {
     // the 2-channel heads (N padded to 16): touch only the two real columns, one 8-byte store per pixel
-    const float a = apply_act<ACT>(__uint_as_float(v[0]) * s_scale[j] + s_shift[j]);
-    const float b = apply_act<ACT>(__uint_as_float(v[1]) * s_scale[j + 1] + s_shift[j + 1]);
+    const float a = apply_act<ACT>(__uint_as_float(v[0]) * lds_f1(s_scale + j) + lds_f1(s_shift + j));
+    const float b = apply_act<ACT>(__uint_as_float(v[1]) * lds_f1(s_scale + j + 1) + lds_f1(s_shift + j + 1));
     *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * 2 + n0) = make_float2(a, b);
     return;
   }
   float f[CW];
 #pragma unroll
-  for (int x = 0; x < CW; ++x) f[x] = __uint_as_float(v[x]) * s_scale[j + x] + s_shift[j + x];
+  for (int x = 0; x < CW; x += 4) {        // per-channel scale / shift as 128-bit shared-memory loads (j is a multiple of 16)
+    const float4 sh = lds_f4(s_shift + j + x);
+    if (p.scale != nullptr) {
+      const float4 sc = lds_f4(s_scale + j + x);
+      f[x] = __uint_as_float(v[x]) * sc.x + sh.x; f[x + 1] = __uint_as_float(v[x + 1]) * sc.y + sh.y;
+      f[x + 2] = __uint_as_float(v[x + 2]) * sc.z + sh.z; f[x + 3] = __uint_as_float(v[x + 3]) * sc.w + sh.w;
+    } else {                                // decoder layers (bias only) and raw outputs: no multiply
+      f[x] = __uint_as_float(v[x]) + sh.x; f[x + 1] = __uint_as_float(v[x + 1]) + sh.y;
+      f[x + 2] = __uint_as_float(v[x + 2]) + sh.z; f[x + 3] = __uint_as_float(v[x + 3]) + sh.w;
+    }
+  }
   const int ncols = min(CW, p.N - n0);
   if (p.residual != nullptr) {
     const uint8_t* rp = p.residual + (static_cast<size_t>(m) * p.res_ld + n0) * 2;
@@ -272,7 +282,7 @@ conv_igemm_kernel(const __grid_constant__ IgemmParams p, const __grid_constant__
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* s_scale = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* s_scale = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~static_cast<uintptr_t>(15));   // float4 loads
   float* s_shift = s_scale + BN;
   uint4* s_rowinfo = reinterpret_cast<uint4*>(s_shift + BN);   // [2][BM] {base0, code0, base1, code1}
   uint32_t* s_ktab = reinterpret_cast<uint32_t*>(s_rowinfo + 2 * BM);   // per 16-byte K chunk: tap/channel decode
@@ -559,7 +569,7 @@ struct StripCfg {
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int MAX_STAGES = 8;
   // everything but the stage ring and the resident filter: alignment slack, mbarriers, TMEM pointer, scale/shift, maps
-  static constexpr int FIXED_BYTES = 1024 + (2 * MAX_STAGES + 5) * 8 + 16 + 2 * BN * 4 + 2 * (2 * STRIP_ROWS + 8) * 4;
+  static constexpr int FIXED_BYTES = 1024 + (2 * MAX_STAGES + 5) * 8 + 32 + 2 * BN * 4 + 2 * (2 * STRIP_ROWS + 8) * 4;
   static constexpr int SMEM_MAX = 232448;      // 227 KB opt-in limit per CTA
 };
 
@@ -604,7 +614,7 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* w_bar = tmem_empty_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
-  float* s_scale = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* s_scale = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~static_cast<uintptr_t>(15));   // float4 loads
   float* s_shift = s_scale + BN;
   // per tile: element offset of every strip pixel inside its source row (0xFFFFFFFF = padding zero), for both
   // sources, and the element offset of the three source rows (double-buffered)
@@ -888,14 +898,28 @@ struct RowStreamParams {
   int total_items;           // batch * tiles_per_row * chunks_per_col
 };
 
+// warp roles of the row-streaming kernel: 4 producer warps (input strips: by TMA one thread suffices, the cp.async gather
+// is not what paces the kernel either), 2 MMA-issuing warps (one per TMEM half / item of the pair), 16 epilogue warps =
+// 4 groups of 4 (one warp per TMEM lane quadrant).  Triage on B200 (scripts/triage_rowstream.py, outconv4.0.conv2
+// forward, 0.37 ms): without the epilogue's math + stores 0.22 ms, without the MMAs 0.30, without the loads 0.33, the
+// bare barrier skeleton 0.11 -- a row's drain is ~330 dependent instructions per thread (bias, ELU = 5 ops with a MUFU,
+// pack, stores), i.e. ~1200 cycles per warp, so the number of rows drained CONCURRENTLY sets the pace: four groups.
+constexpr int RS_PRODUCER_WARPS = 4;
+constexpr int RS_PRODUCER_THREADS = RS_PRODUCER_WARPS * 32;
+constexpr int RS_MMA_WARP = RS_PRODUCER_WARPS;                            // warps 4, 5
+constexpr int RS_EPI_FIRST_WARP = RS_MMA_WARP + 2;
+constexpr int RS_EPI_WARPS = 16;
+constexpr int RS_EPI_THREADS = RS_EPI_WARPS * 32;
+constexpr int RS_THREADS = (RS_EPI_FIRST_WARP + RS_EPI_WARPS) * 32;       // 704
+
 template <int BN, int CB>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(RS_THREADS, 1)
 conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_constant__ CUtensorMap tmap_w,
                       const __grid_constant__ CUtensorMap tmap_x) {
   using Cfg = StripCfg<BN, CB>;
   constexpr int ROW_BYTES = Cfg::ROW_BYTES;
   constexpr int CPR = ROW_BYTES / 16;
-  constexpr int ROWS_PER_PASS = NUM_PRODUCER_THREADS / CPR;
+  constexpr int ROWS_PER_PASS = RS_PRODUCER_THREADS / CPR;
   constexpr uint64_t LAYOUT = (CB == 64) ? 2ull : 4ull;
   constexpr uint32_t SBO = 8 * ROW_BYTES;
   constexpr int MAX_STAGES = Cfg::MAX_STAGES;
@@ -916,9 +940,9 @@ conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_c
   uint64_t* row_empty = row_full + SLOTS;                               // [SLOTS] epilogue -> MMA
   uint64_t* w_bar = row_empty + SLOTS;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
-  float* s_scale = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* s_scale = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~static_cast<uintptr_t>(15));   // float4 loads
   float* s_shift = s_scale + BN;
-  uint32_t* s_xoff = reinterpret_cast<uint32_t*>(s_shift + BN);        // [2][2*STRIP_ROWS] column maps of both sources
+  uint32_t* s_xoff = reinterpret_cast<uint32_t*>(s_shift + BN);        // [2 pair parities][2 items][2*STRIP_ROWS] column maps
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -926,12 +950,12 @@ conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_c
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], rp.x_via_tma ? 1 : NUM_PRODUCER_THREADS);
+      mbar_init(&full_bar[s], rp.x_via_tma ? 1 : RS_PRODUCER_THREADS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int q = 0; q < SLOTS; ++q) {
       mbar_init(&row_full[q], 1);
-      mbar_init(&row_empty[q], NUM_EPI_WARPS);
+      mbar_init(&row_empty[q], NUM_EPI_WARPS / 2);         // the four warps of the group that drains this row
     }
     mbar_init(w_bar, 1);
     fence_barrier_init();
@@ -945,7 +969,7 @@ conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_c
           tma_load_2d(smem_u32(w_res) + ((dx * rp.cblocks + cb) * 3 + dy) * Cfg::B_TILE, &tmap_w, w_bar,
                       ((dy * 3 + dx) * rp.cblocks + cb) * CB, 0);
   }
-  if (warp == MMA_WARP) tmem_alloc(tmem_ptr_smem, 512);
+  if (warp == RS_MMA_WARP) tmem_alloc(tmem_ptr_smem, 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -960,76 +984,109 @@ conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_c
     yc = chunk * H;
   };
 
-  if (warp < NUM_PRODUCER_WARPS && rp.x_via_tma) {
+  // A CTA works on PAIRS of items at once: item 2*pair + sub lives in TMEM half `sub`, is issued by MMA warp `sub` and
+  // drained by epilogue group `sub`; the producers alternate the two items' rows through one stage ring (even stages =
+  // sub 0, odd = sub 1).  Why two issuers: on the thin layers a row costs 6-12 tcgen05.mma (~340-700 tensor cycles) but
+  // the ~150 dependent instructions one thread spends per row (waits, descriptor arithmetic, the ELECT wrappers ptxas
+  // puts around each MMA) took ~1300 cycles (ncu r02j: tensor pipe 18-29 %, DRAM 18-31 %, 8.4 cycles per issued
+  // instruction): the single issuing thread, not the tensor pipe or memory, paced the kernel.
+  const int total_pairs = (rp.total_items + 1) >> 1;
+
+  if (warp < RS_PRODUCER_WARPS && rp.x_via_tma) {
     // =============================== PRODUCER (TMA) ===============================
     if (tid == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int item = blockIdx.x; item < rp.total_items; item += gridDim.x) {
-        int img, x0, yc;
-        decode(item, img, x0, yc);
+      for (int pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) {
+        int img[2], x0[2], yc[2];
+        bool ex[2];
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          ex[sub] = 2 * pair + sub < rp.total_items;
+          decode(ex[sub] ? 2 * pair + sub : 2 * pair, img[sub], x0[sub], yc[sub]);
+        }
         for (int j = 0; j < H + 2; ++j)
-          for (int cb = 0; cb < rp.cblocks; ++cb) {
-            mbar_wait(&empty_bar[s], ph ^ 1, 41);
-            mbar_arrive_expect_tx(&full_bar[s], STRIP_PIX * ROW_BYTES);
-            tma_load_4d(smem_u32(stage0) + s * Cfg::A_BYTES, &tmap_x, &full_bar[s], cb * CB, x0 - g.pad_l,
-                        yc - g.pad_t + j, img);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-          }
+          for (int cb = 0; cb < rp.cblocks; ++cb)
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              mbar_wait(&empty_bar[s], ph ^ 1, 41);
+              if (ex[sub] && !(kTriage && (p.debug & 1))) {
+                mbar_arrive_expect_tx(&full_bar[s], STRIP_PIX * ROW_BYTES);
+                tma_load_4d(smem_u32(stage0) + s * Cfg::A_BYTES, &tmap_x, &full_bar[s], cb * CB, x0[sub] - g.pad_l,
+                            yc[sub] - g.pad_t + j, img[sub]);
+              } else {
+                mbar_arrive(&full_bar[s]);                 // odd item count: the missing partner's stages stay empty
+              }
+              if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
       }
     }
-  } else if (warp < NUM_PRODUCER_WARPS) {
+  } else if (warp < RS_PRODUCER_WARPS) {
     // =============================== PRODUCERS (cp.async) ===============================
     const int c = tid % CPR;
     const int r0 = tid / CPR;
     int s = 0;
-    uint32_t ph = 0, it = 0;
-    for (int item = blockIdx.x; item < rp.total_items; item += gridDim.x, ++it) {
-      int img, x0, yc;
-      decode(item, img, x0, yc);
-      uint32_t* xo = s_xoff + (it & 1) * (2 * STRIP_ROWS);
-      if (tid < STRIP_ROWS) {
-        int vx = x0 - g.pad_l + tid;
-        bool ok = tid < STRIP_PIX;
-        if (g.pad_mode == FP_PAD_REFLECT) vx = vx < 0 ? -vx : (vx >= g.Win ? 2 * g.Win - 2 - vx : vx);
-        ok = ok && static_cast<unsigned>(vx) < static_cast<unsigned>(g.Win);
-        xo[tid] = ok ? static_cast<uint32_t>((g.up0 ? vx >> 1 : vx) * g.C0) : 0xFFFFFFFFu;
-        xo[STRIP_ROWS + tid] = ok ? static_cast<uint32_t>(vx * g.C1) : 0xFFFFFFFFu;
-      }
-      named_bar_sync(2, NUM_PRODUCER_THREADS);
-      for (int j = 0; j < H + 2; ++j) {
-        int vy = yc - g.pad_t + j;
-        if (g.pad_mode == FP_PAD_REFLECT) vy = vy < 0 ? -vy : (vy >= g.Hin ? 2 * g.Hin - 2 - vy : vy);
-        const bool row_ok = static_cast<unsigned>(vy) < static_cast<unsigned>(g.Hin);   // rows past a ragged item: zeros
-        const uint32_t rowoff0 = static_cast<uint32_t>(((img * g.H0 + (g.up0 ? vy >> 1 : vy)) * g.W0) * g.C0);
-        const uint32_t rowoff1 = static_cast<uint32_t>(((img * g.Hin + vy) * g.Win) * g.C1);
-        for (int cb = 0; cb < rp.cblocks; ++cb) {
-          mbar_wait(&empty_bar[s], ph ^ 1, 42);
-          const uint32_t stage = smem_u32(stage0) + s * Cfg::A_BYTES;
-          const int ch = cb * CB;
-          const bool second = ch >= g.C0;
-          const uint8_t* sbase = second ? g.src1 : g.src0;
-          const uint32_t rowoff = second ? rowoff1 : rowoff0;
-          const uint32_t* xcol = xo + (second ? STRIP_ROWS : 0);
-          const uint32_t cc = static_cast<uint32_t>(second ? ch - g.C0 : ch) + c * 8;
+    uint32_t ph = 0, pit = 0;
+    for (int pair = blockIdx.x; pair < total_pairs; pair += gridDim.x, ++pit) {
+      int img[2], x0[2], yc[2];
+      bool ex[2];
 #pragma unroll
-          for (int i = 0; i < (STRIP_PIX + ROWS_PER_PASS - 1) / ROWS_PER_PASS; ++i) {
-            const int r = r0 + ROWS_PER_PASS * i;
-            if (r < STRIP_PIX) {
-              const uint32_t xoff = xcol[r];
-              const bool ok = row_ok && (xoff != 0xFFFFFFFFu);
-              const uint32_t off = ok ? rowoff + xoff + cc : 0u;
-              const int sw = (CB == 64) ? (c ^ (r & 7)) : (c ^ ((r >> 1) & 3));
-              cp_async_16_zfill(stage + r * ROW_BYTES + (sw << 4), sbase + static_cast<size_t>(off) * 2, ok);
+      for (int sub = 0; sub < 2; ++sub) {
+        ex[sub] = 2 * pair + sub < rp.total_items;
+        decode(ex[sub] ? 2 * pair + sub : 2 * pair, img[sub], x0[sub], yc[sub]);
+      }
+      uint32_t* xo2 = s_xoff + (pit & 1) * (4 * STRIP_ROWS);       // [sub][2 * STRIP_ROWS]
+      for (int t = tid; t < STRIP_ROWS; t += RS_PRODUCER_THREADS) {
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          int vx = x0[sub] - g.pad_l + t;
+          bool ok = t < STRIP_PIX;
+          if (g.pad_mode == FP_PAD_REFLECT) vx = vx < 0 ? -vx : (vx >= g.Win ? 2 * g.Win - 2 - vx : vx);
+          ok = ok && static_cast<unsigned>(vx) < static_cast<unsigned>(g.Win);
+          xo2[sub * 2 * STRIP_ROWS + t] = ok ? static_cast<uint32_t>((g.up0 ? vx >> 1 : vx) * g.C0) : 0xFFFFFFFFu;
+          xo2[sub * 2 * STRIP_ROWS + STRIP_ROWS + t] = ok ? static_cast<uint32_t>(vx * g.C1) : 0xFFFFFFFFu;
+        }
+      }
+      named_bar_sync(2, RS_PRODUCER_THREADS);
+      for (int j = 0; j < H + 2; ++j) {
+        for (int cb = 0; cb < rp.cblocks; ++cb) {
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            mbar_wait(&empty_bar[s], ph ^ 1, 42);
+            if (ex[sub] && !(kTriage && (p.debug & 1))) {
+              int vy = yc[sub] - g.pad_t + j;
+              if (g.pad_mode == FP_PAD_REFLECT) vy = vy < 0 ? -vy : (vy >= g.Hin ? 2 * g.Hin - 2 - vy : vy);
+              const bool row_ok = static_cast<unsigned>(vy) < static_cast<unsigned>(g.Hin);   // rows past a ragged item: zeros
+              const uint32_t* xo = xo2 + sub * 2 * STRIP_ROWS;
+              const uint32_t stage = smem_u32(stage0) + s * Cfg::A_BYTES;
+              const int ch = cb * CB;
+              const bool second = ch >= g.C0;
+              const uint8_t* sbase = second ? g.src1 : g.src0;
+              const uint32_t rowoff = second ? static_cast<uint32_t>(((img[sub] * g.Hin + vy) * g.Win) * g.C1)
+                                             : static_cast<uint32_t>(((img[sub] * g.H0 + (g.up0 ? vy >> 1 : vy)) * g.W0) * g.C0);
+              const uint32_t* xcol = xo + (second ? STRIP_ROWS : 0);
+              const uint32_t cc = static_cast<uint32_t>(second ? ch - g.C0 : ch) + c * 8;
+#pragma unroll
+              for (int i = 0; i < (STRIP_PIX + ROWS_PER_PASS - 1) / ROWS_PER_PASS; ++i) {
+                const int r = r0 + ROWS_PER_PASS * i;
+                if (r < STRIP_PIX) {
+                  const uint32_t xoff = xcol[r];
+                  const bool ok = row_ok && (xoff != 0xFFFFFFFFu);
+                  const uint32_t off = ok ? rowoff + xoff + cc : 0u;
+                  const int sw = (CB == 64) ? (c ^ (r & 7)) : (c ^ ((r >> 1) & 3));
+                  cp_async_16_zfill(stage + r * ROW_BYTES + (sw << 4), sbase + static_cast<size_t>(off) * 2, ok);
+                }
+              }
             }
+            cp_async_mbar_arrive_noinc(&full_bar[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
-          cp_async_mbar_arrive_noinc(&full_bar[s]);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == MMA_WARP) {
-    // =============================== MMA ISSUER ===============================
+  } else if (warp < RS_EPI_FIRST_WARP) {
+    // =============================== MMA ISSUERS (one warp per TMEM half) ===============================
+    const int half = warp - RS_MMA_WARP;
     if (lane == 0) {
       const uint32_t idesc1 = umma_idesc_f16(BM, BN, p.fmt, p.w_fmt, 0, 0);
       const uint32_t idesc2 = umma_idesc_f16(BM, 2 * BN, p.fmt, p.w_fmt, 0, 0);
@@ -1039,19 +1096,19 @@ conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_c
       const uint32_t stage0_lo = ((smem_u32(stage0) >> 4) & 0x3FFF) | (1u << 16);
       const uint32_t wres_lo = ((smem_u32(w_res) >> 4) & 0x3FFF) | (1u << 16);
       constexpr uint32_t BT = Cfg::B_TILE >> 4;
-      int s = 0;
-      uint32_t ph = 0, it = 0;
+      int s = half;                                          // this warp's stages: half, half + 2, ...
+      uint32_t ph = 0, pit = 0;
       mbar_wait(w_bar, 0, 43);
-      for (int item = blockIdx.x; item < rp.total_items; item += gridDim.x, ++it) {
-        const uint32_t half = it & 1;
-        const uint32_t use_par = (it >> 1) & 1;            // parity of this half's use count
+      for (int pair = blockIdx.x; pair < total_pairs; pair += gridDim.x, ++pit) {
+        const bool ex = 2 * pair + half < rp.total_items;
+        const uint32_t use_par = pit & 1;                    // parity of this half's use count
         for (int j = 0; j < H + 2; ++j) {
           const int dy_lo = j > H - 1 ? j - (H - 1) : 0;
           const int dy_hi = j < 2 ? j : 2;
           const int ndy = dy_hi - dy_lo + 1;
           const int q_hi = (H - 1) - (j - dy_lo);          // slot of the dy_lo block's output row
           const uint32_t d_col = tmem_base + (half * H + q_hi) * BN;
-          if (dy_lo == 0) {                                // first touch of this row slot in this item
+          if (ex && dy_lo == 0) {                          // first touch of this row slot in this item
             mbar_wait(&row_empty[half * H + q_hi], use_par ^ 1, 44);
             tcgen05_fence_after();
           }
@@ -1060,63 +1117,63 @@ conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_c
           for (int cb = 0; cb < rp.cblocks; ++cb) {
             mbar_wait(&full_bar[s], ph, 45);
             tcgen05_fence_after();
-            const uint32_t a_lo = stage0_lo + static_cast<uint32_t>(s) * (Cfg::A_BYTES >> 4);
+            if (ex && !(kTriage && (p.debug & 2))) {
+              const uint32_t a_lo = stage0_lo + static_cast<uint32_t>(s) * (Cfg::A_BYTES >> 4);
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const uint32_t b_lo = wres_lo + ((dx * rp.cblocks + cb) * 3 + dy_lo) * BT;
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint32_t b_lo = wres_lo + ((dx * rp.cblocks + cb) * 3 + dy_lo) * BT;
 #pragma unroll
-              for (int k = 0; k < CB / 16; ++k) {
-                const uint64_t a_desc = mk_desc(a_lo + dx * (ROW_BYTES >> 4) + 2 * k);
-                if (dy_lo == 0 && cb == 0 && dx == 0 && k == 0) {
-                  umma_f16(d_col, a_desc, mk_desc(b_lo), idesc1, 0u);                       // opens the row's accumulator
-                  if (ndy > 1) umma_f16(d_col + BN, a_desc, mk_desc(b_lo + BT), idesc_rest, 1u);
-                } else {
-                  umma_f16(d_col, a_desc, mk_desc(b_lo + 2 * k), idesc_n, 1u);
+                for (int k = 0; k < CB / 16; ++k) {
+                  const uint64_t a_desc = mk_desc(a_lo + dx * (ROW_BYTES >> 4) + 2 * k);
+                  if (dy_lo == 0 && cb == 0 && dx == 0 && k == 0) {
+                    umma_f16(d_col, a_desc, mk_desc(b_lo), idesc1, 0u);                       // opens the row's accumulator
+                    if (ndy > 1) umma_f16(d_col + BN, a_desc, mk_desc(b_lo + BT), idesc_rest, 1u);
+                  } else {
+                    umma_f16(d_col, a_desc, mk_desc(b_lo + 2 * k), idesc_n, 1u);
+                  }
                 }
               }
             }
             umma_commit(&empty_bar[s]);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
+            s += 2;
+            if (s >= STAGES) { s -= STAGES; ph ^= 1; }
           }
-          if (j >= 2) umma_commit(&row_full[half * H + (H - 1) - (j - 2)]);   // output row yc + j - 2 is complete
+          if (ex && j >= 2) umma_commit(&row_full[half * H + (H - 1) - (j - 2)]);   // output row yc + j - 2 is complete
         }
       }
     }
     __syncwarp();
   } else {
     // =============================== EPILOGUE ===============================
+    // four groups of four warps (one warp per TMEM lane quadrant): group grp drains the rows r = (grp >> 1) (mod 2) of the
+    // pair's item hf = grp & 1
     const int q = warp & 3;
-    const int hf = (warp - EPI_FIRST_WARP) >> 2;
+    const int grp = (warp - RS_EPI_FIRST_WARP) >> 2;
+    const int hf = grp & 1;
     const int row = q * 32 + lane;
-    const int e = tid - EPI_FIRST_WARP * 32;
-    constexpr int COLS_PER_HALF = (BN >= 32) ? BN / 2 : BN;      // BN = 16 (the 2-channel heads): one 16-column drain
-    const int col_begin = (BN >= 32) ? hf * COLS_PER_HALF : 0;
-    const bool active = (BN >= 32) || (hf == 0);
-    for (int j = e; j < BN; j += NUM_EPI_THREADS) {
+    const int e = tid - RS_EPI_FIRST_WARP * 32;
+    for (int j = e; j < BN; j += RS_EPI_THREADS) {
       s_scale[j] = (p.scale != nullptr && j < p.N) ? p.scale[j] : 1.f;
       s_shift[j] = (p.shift != nullptr && j < p.N) ? p.shift[j] : 0.f;
     }
-    named_bar_sync(1, NUM_EPI_THREADS);
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < rp.total_items; item += gridDim.x, ++it) {
+    named_bar_sync(1, RS_EPI_THREADS);
+    uint32_t pit = 0;
+    for (int pair = blockIdx.x; pair < total_pairs; pair += gridDim.x, ++pit) {
+      const int item = 2 * pair + hf;
+      if (item >= rp.total_items) continue;
       int img, x0, yc;
       decode(item, img, x0, yc);
-      const uint32_t half = it & 1;
-      const uint32_t use_par = (it >> 1) & 1;
-      for (int r = 0; r < H; ++r) {
-        const int slot = half * H + (H - 1 - r);
+      const uint32_t use_par = pit & 1;
+      for (int r = grp >> 1; r < H; r += 2) {
+        const int slot = hf * H + (H - 1 - r);
         const int y = yc + r;
         mbar_wait<32>(&row_full[slot], use_par, 46);
         tcgen05_fence_after();
         const int m = (img * g.Ho + y) * g.Wo + x0 + row;
-        const bool m_ok = (x0 + row) < g.Wo && y < g.Ho;
+        const bool m_ok = (x0 + row) < g.Wo && y < g.Ho && !(kTriage && (p.debug & 4));
         const uint32_t tbase = tmem_base + slot * BN + (static_cast<uint32_t>(q * 32) << 16);
-#define FP_EPI(A, F) epilogue_cols<A, F, COLS_PER_HALF>(p, tbase, col_begin, 0, m, m_ok, s_scale, s_shift, &row_empty[slot], lane)
-        if (!active) {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&row_empty[slot]);
-        } else if (p.fmt == FP_BF16) {
+#define FP_EPI(A, F) epilogue_cols<A, F, BN>(p, tbase, 0, 0, m, m_ok, s_scale, s_shift, &row_empty[slot], lane)
+        if (p.fmt == FP_BF16) {
           switch (p.act) {
             case FP_ACT_RELU: FP_EPI(FP_ACT_RELU, FP_BF16); break;
             case FP_ACT_ELU: FP_EPI(FP_ACT_ELU, FP_BF16); break;
@@ -1138,7 +1195,7 @@ conv_rowstream_kernel(const __grid_constant__ RowStreamParams rp, const __grid_c
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == RS_MMA_WARP) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -1179,7 +1236,7 @@ template <int BN, int CB>
 static int launch_rowstream(const StripParams& sp, const CUtensorMap& tmap, const CUtensorMap& tmap_x, cudaStream_t stream) {
   using Cfg = StripCfg<BN, CB>;
   constexpr int SLOTS = 512 / BN;
-  constexpr int RS_FIXED = 1024 + (2 * Cfg::MAX_STAGES + 2 * SLOTS + 1) * 8 + 16 + 2 * BN * 4 + 2 * 2 * STRIP_ROWS * 4;
+  constexpr int RS_FIXED = 1024 + (2 * Cfg::MAX_STAGES + 2 * SLOTS + 1) * 8 + 32 + 2 * BN * 4 + 2 * 4 * STRIP_ROWS * 4;
   RowStreamParams rp{};
   rp.b = sp.b;
   rp.tiles_per_row = sp.tiles_per_row;
@@ -1187,16 +1244,17 @@ static int launch_rowstream(const StripParams& sp, const CUtensorMap& tmap, cons
   rp.x_via_tma = sp.x_via_tma;
   rp.w_bytes = 9 * sp.cblocks * Cfg::B_TILE;
   const int room = Cfg::SMEM_MAX - RS_FIXED - rp.w_bytes;
-  if (sp.b.n_tiles != 1 || room < 3 * Cfg::A_BYTES) return FP_ERR_UNSUPPORTED;
-  rp.stages = room / Cfg::A_BYTES < Cfg::MAX_STAGES ? room / Cfg::A_BYTES : Cfg::MAX_STAGES;
+  if (sp.b.n_tiles != 1 || room < 4 * Cfg::A_BYTES) return FP_ERR_UNSUPPORTED;
+  rp.stages = (room / Cfg::A_BYTES < Cfg::MAX_STAGES ? room / Cfg::A_BYTES : Cfg::MAX_STAGES) & ~1;   // even: the two MMA warps own alternate stages
   rp.H = SLOTS / 2;
   rp.chunks_per_col = (sp.b.g.Ho + rp.H - 1) / rp.H;
   rp.total_items = sp.b.g.M / sp.b.g.HoWo * sp.tiles_per_row * rp.chunks_per_col;
   auto kern = conv_rowstream_kernel<BN, CB>;
   { const int arc = ensure_max_smem(reinterpret_cast<const void*>(kern), Cfg::SMEM_MAX, "kern"); if (arc != FP_OK) return arc; }
   const int smem_bytes = RS_FIXED + rp.stages * Cfg::A_BYTES + rp.w_bytes;
-  const int grid = rp.total_items < num_sms() ? rp.total_items : num_sms();
-  kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(rp, tmap, tmap_x);
+  const int pairs = (rp.total_items + 1) / 2;
+  const int grid = pairs < num_sms() ? pairs : num_sms();
+  kern<<<grid, RS_THREADS, smem_bytes, stream>>>(rp, tmap, tmap_x);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FP_ERR_CUDA, "conv_rowstream launch (BN=%d): %s", BN, cudaGetErrorString(e));
   return FP_OK;

@@ -813,6 +813,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int split
   const float* src = partial + static_cast<size_t>(co) * kpad + k;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;        // four independent chains, fixed order
   int sp = 0;
+#pragma unroll 4                                          // 16 loads in flight: the kernel is pure load latency
   for (; sp + 4 <= splits; sp += 4) {
     s0 += src[(sp + 0) * stride]; s1 += src[(sp + 1) * stride]; s2 += src[(sp + 2) * stride]; s3 += src[(sp + 3) * stride];
   }

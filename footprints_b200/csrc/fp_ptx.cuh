@@ -255,6 +255,20 @@ __device__ __forceinline__ uint32_t f32x2_to_f16x2_sat(float a, float b) {
   return r;
 }
 
+// 128-bit shared-memory load through the .shared window: a `const float*` that only the programmer knows to be shared
+// memory compiles to a GENERIC load (LD.E + descriptor set-up via R2UR) -- four extra instructions per load in the
+// convolution epilogues
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ float lds_f1(const float* p) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+  return v;
+}
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

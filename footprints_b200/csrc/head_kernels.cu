@@ -565,6 +565,90 @@ head_wgrad_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dz8, in
   }
 }
 
+// Tiled stage 1 (default): a persistent block walks 8 x 32-pixel tiles; the input tile with its reflected halo
+// ((8+2) x (32+2) pixels x C channels) and the tile's dZ pairs are staged in shared memory ONCE, so the nine taps read
+// shared memory instead of re-reading global memory nine times.  thread = (pixel group g, tap t, 8-channel chunk cc)
+// keeps its 2 x 8 sums in registers across all its tiles; one fixed-order reduction over g at the end.
+// Same partial layout as head_wgrad_kernel.  The 2-channel heads on the tensor-core weight-gradient kernel cost as much
+// as a 32-channel layer (the cost is staging X and issuing MMAs, 126 of 128 M rows are padding): this kernel is ~2x faster.
+constexpr int HW_TH = 8, HW_TW = 32;
+__global__ void __launch_bounds__(HEAD_THREADS)
+head_wgrad_tile_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dz8, int batch, int H, int W, int C, int act_fmt,
+                       int grad_fmt, int tiles_x, int tiles_y, float* __restrict__ partial) {
+  extern __shared__ uint4 hw_smem[];
+  const int c8 = C >> 3;
+  uint4* sx = hw_smem;                                              // [(TH+2)*(TW+2)][c8]
+  float2* sdz = reinterpret_cast<float2*>(sx + (HW_TH + 2) * (HW_TW + 2) * c8);   // [TH*TW]
+  float* red = reinterpret_cast<float*>(sdz + HW_TH * HW_TW);         // [groups][lanes][16] (reused at the end)
+  const int lanes = 9 * c8;
+  const int groups = HEAD_THREADS / lanes;
+  const int g = threadIdx.x / lanes, l = threadIdx.x - g * lanes;
+  const int t = l / c8, cc = l - t * c8;
+  const int ty = t / 3, tx = t - ty * 3;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  float b0 = 0.f, b1 = 0.f;
+  const int tiles_per_img = tiles_x * tiles_y;
+  const int total = batch * tiles_per_img;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int img = tile / tiles_per_img;
+    const int r = tile - img * tiles_per_img;
+    const int y0 = (r / tiles_x) * HW_TH, x0 = (r % tiles_x) * HW_TW;
+    __syncthreads();                                                 // previous tile fully consumed
+    for (int i = threadIdx.x; i < (HW_TH + 2) * (HW_TW + 2) * c8; i += HEAD_THREADS) {
+      const int ch = i % c8, pp = i / c8;
+      const int py = pp / (HW_TW + 2), px = pp - py * (HW_TW + 2);
+      const int yy = reflect1(min(y0 + py - 1, H), H), xx = reflect1(min(x0 + px - 1, W), W);   // (clamped: rows/cols past a
+      sx[i] = x[((static_cast<long long>(img) * H + yy) * W + xx) * c8 + ch];                   //  ragged tile pair with dz = 0)
+    }
+    for (int i = threadIdx.x; i < HW_TH * HW_TW; i += HEAD_THREADS) {
+      const int py = i / HW_TW, px = i - py * HW_TW;
+      float2 d = make_float2(0.f, 0.f);
+      if (y0 + py < H && x0 + px < W)
+        d = h_up2(reinterpret_cast<const uint32_t*>(dz8 + (static_cast<long long>(img) * H + y0 + py) * W + x0 + px)[0], grad_fmt);
+      sdz[i] = d;
+    }
+    __syncthreads();
+    if (g < groups) {
+      for (int p = g; p < HW_TH * HW_TW; p += groups) {
+        const int py = p / HW_TW, px = p - py * HW_TW;
+        const float2 d = sdz[p];
+        float f[8];
+        h_unpack8(sx[((py + ty) * (HW_TW + 2) + px + tx) * c8 + cc], act_fmt, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i] = fmaf(f[i], d.x, acc[i]);
+          acc[8 + i] = fmaf(f[i], d.y, acc[8 + i]);
+        }
+        if (l == 0) { b0 += d.x; b1 += d.y; }
+      }
+    }
+  }
+  __syncthreads();
+  if (g < groups) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) red[(g * lanes + l) * 16 + i] = acc[i];
+  }
+  __shared__ float redb2[HEAD_THREADS / 9][2];
+  if (g < groups && l == 0) { redb2[g][0] = b0; redb2[g][1] = b1; }
+  __syncthreads();
+  float* out = partial + static_cast<long long>(blockIdx.x) * (2 * C * 9 + 2);
+  for (int i = threadIdx.x; i < lanes * 16; i += HEAD_THREADS) {
+    const int ll = i >> 4, j = i & 15;
+    float s = 0.f;
+    for (int gg = 0; gg < groups; ++gg) s += red[(gg * lanes + ll) * 16 + j];
+    const int t2 = ll / c8, cc2 = ll - t2 * c8;
+    const int co = j >> 3, c = cc2 * 8 + (j & 7);
+    out[(co * C + c) * 9 + t2] = s;
+  }
+  if (threadIdx.x < 2) {
+    float s = 0.f;
+    for (int gg = 0; gg < groups; ++gg) s += redb2[gg][threadIdx.x];
+    out[2 * C * 9 + threadIdx.x] = s;
+  }
+}
+
 // Stage 2: fixed-order sum over blocks
 __global__ void head_wgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int n, int accumulate,
                                          float* __restrict__ dw, float* __restrict__ db) {
@@ -646,16 +730,29 @@ extern "C" int fp_head_conv_wgrad(const void* x, const void* dz8, int batch, int
   if (!x || !dz8 || !dw_oihw || !dbias || !workspace) return set_error(FP_ERR_ARG, "fp_head_conv_wgrad: null argument");
   int rc = head_check("fp_head_conv_wgrad", c, h, w);
   if (rc != FP_OK) return rc;
-  const long long P = static_cast<long long>(batch) * h * w;
   const int lanes = 9 * (c / 8);
   if (lanes > HEAD_THREADS) return set_error(FP_ERR_UNSUPPORTED, "fp_head_conv_wgrad: C too large");
   const int groups = HEAD_THREADS / lanes;
-  long long want = (P + 4095) / 4096;
-  const int nblk = static_cast<int>(want < 1 ? 1 : (want > 1184 ? 1184 : want));
-  const long long ppb = (P + nblk - 1) / nblk;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  head_wgrad_kernel<<<nblk, HEAD_THREADS, groups * lanes * 16 * sizeof(float), st>>>(
-      static_cast<const uint4*>(x), static_cast<const uint4*>(dz8), batch, h, w, c, act_dtype, grad_dtype, ppb, workspace);
+  int nblk;
+  if (opts().head_tile != 0) {
+    const int tiles_x = (w + HW_TW - 1) / HW_TW, tiles_y = (h + HW_TH - 1) / HW_TH;
+    const long long tiles = static_cast<long long>(batch) * tiles_x * tiles_y;
+    const int smem = (HW_TH + 2) * (HW_TW + 2) * (c / 8) * 16 + HW_TH * HW_TW * 8 + groups * lanes * 16 * 4;
+    const int per_sm = smem > 100 * 1024 ? 2 : (smem > 56 * 1024 ? 3 : 4);
+    nblk = static_cast<int>(tiles < per_sm * num_sms() ? tiles : per_sm * num_sms());
+    if (nblk > 1184) nblk = 1184;
+    { const int arc = ensure_max_smem(reinterpret_cast<const void*>(head_wgrad_tile_kernel), 200 * 1024, "head_wgrad_tile_kernel"); if (arc != FP_OK) return arc; }
+    head_wgrad_tile_kernel<<<nblk, HEAD_THREADS, smem, st>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(dz8), batch, h, w,
+                                                            c, act_dtype, grad_dtype, tiles_x, tiles_y, workspace);
+  } else {
+    const long long P = static_cast<long long>(batch) * h * w;
+    long long want = (P + 4095) / 4096;
+    nblk = static_cast<int>(want < 1 ? 1 : (want > 1184 ? 1184 : want));
+    const long long ppb = (P + nblk - 1) / nblk;
+    head_wgrad_kernel<<<nblk, HEAD_THREADS, groups * lanes * 16 * sizeof(float), st>>>(
+        static_cast<const uint4*>(x), static_cast<const uint4*>(dz8), batch, h, w, c, act_dtype, grad_dtype, ppb, workspace);
+  }
   FP_CHECK_LAUNCH("fp_head_conv_wgrad");
   const int n = 2 * c * 9;
   head_wgrad_reduce_kernel<<<(n + 2 + 127) / 128, 128, 0, st>>>(workspace, nblk, n, accumulate, dw_oihw, dbias);

@@ -132,13 +132,15 @@ col_reduce_kernel(const uint4* __restrict__ a, int a_fmt, const uint4* __restric
   }
 }
 
-// Second stage of the column reductions: one warp per channel sums the per-block partials (lanes stride over the
-// blocks in a fixed order, fp64, then a shuffle tree) — deterministic and ~30x faster than one thread per channel.
-__device__ __forceinline__ void warp_sum_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s,
-                                                  double& q) {
-  const int lane = threadIdx.x & 31;
+// Second stage of the column reductions: one 128-thread block per channel sums the per-block partials (threads stride
+// over the blocks, fp64, shuffle tree per warp, then the four warp sums in order) -- deterministic.  These kernels are
+// pure latency (<= 1184 partials per channel): 128 threads per channel keep the dependent-load chains <= 10 long.
+constexpr int SUM_THREADS = 128;
+__device__ __forceinline__ void block_sum_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s,
+                                                   double& q) {
+  __shared__ double sh[2][SUM_THREADS / 32];
   s = 0.0; q = 0.0;
-  for (int b = lane; b < nblk; b += 32) {
+  for (int b = threadIdx.x; b < nblk; b += SUM_THREADS) {
     s += partial[(static_cast<long long>(b) * 2 + 0) * C + c];
     q += partial[(static_cast<long long>(b) * 2 + 1) * C + c];
   }
@@ -147,6 +149,10 @@ __device__ __forceinline__ void warp_sum_partials(const float* __restrict__ part
     s += __shfl_xor_sync(0xffffffffu, s, off);
     q += __shfl_xor_sync(0xffffffffu, q, off);
   }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  s = (sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3]);
+  q = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
 }
 
 // BatchNorm2d training statistics (torch.nn.functional.batch_norm, training=True): biased variance for
@@ -156,11 +162,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, 
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per channel
-  if (c >= C) return;
+  const int c = blockIdx.x;                                        // one block per channel
   double s, q;
-  warp_sum_partials(partial, nblk, C, c, s, q);
-  if ((threadIdx.x & 31) != 0) return;
+  block_sum_partials(partial, nblk, C, c, s, q);
+  if (threadIdx.x != 0) return;
   const double n = static_cast<double>(M);
   const double mean = s / n;
   double var = q / n - mean * mean;
@@ -181,11 +186,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, 
 // sums the [nblk][2][C] partials: out0[c] = sum row 0, out1[c] = sum row 1 (fp64 accumulate)
 __global__ void partial_sum_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out0,
                                    float* __restrict__ out1) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per channel
-  if (c >= C) return;
+  const int c = blockIdx.x;                                        // one block per channel
   double s, q;
-  warp_sum_partials(partial, nblk, C, c, s, q);
-  if ((threadIdx.x & 31) != 0) return;
+  block_sum_partials(partial, nblk, C, c, s, q);
+  if (threadIdx.x != 0) return;
   if (out0 != nullptr) out0[c] = static_cast<float>(s);
   if (out1 != nullptr) out1[c] = static_cast<float>(q);
 }
@@ -648,7 +652,7 @@ extern "C" int fp_bn_stats(const void* z, long long M, int C, int dtype, const f
   col_reduce_kernel<0><<<nblk, RED_THREADS, rows_per_pass * 2 * C * sizeof(float), st>>>(
       static_cast<const uint4*>(z), dtype, nullptr, nullptr, dtype, nullptr, nullptr, M, C, workspace);
   FP_CHECK_LAUNCH("fp_bn_stats(reduce)");
-  bn_finalize_kernel<<<nblocks(static_cast<long long>(C) * 32, 256), 256, 0, st>>>(workspace, nblk, M, C, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<C, SUM_THREADS, 0, st>>>(workspace, nblk, M, C, gamma, beta, running_mean, running_var,
                                                       momentum, eps, scale, shift, save_mean, save_invstd);
   FP_CHECK_LAUNCH("fp_bn_stats(finalize)");
   return FP_OK;
@@ -667,7 +671,7 @@ extern "C" int fp_bn_stats_split(const void* z_hi, const void* z_lo, long long M
   col_reduce_kernel<0><<<nblk, RED_THREADS, rows_per_pass * 2 * C * sizeof(float), st>>>(
       static_cast<const uint4*>(z_hi), dtype, static_cast<const uint4*>(z_lo), nullptr, dtype, nullptr, nullptr, M, C, workspace);
   FP_CHECK_LAUNCH("fp_bn_stats_split(reduce)");
-  bn_finalize_kernel<<<nblocks(static_cast<long long>(C) * 32, 256), 256, 0, st>>>(workspace, nblk, M, C, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<C, SUM_THREADS, 0, st>>>(workspace, nblk, M, C, gamma, beta, running_mean, running_var,
                                                       momentum, eps, scale, shift, save_mean, save_invstd);
   FP_CHECK_LAUNCH("fp_bn_stats_split(finalize)");
   return FP_OK;
@@ -710,7 +714,7 @@ extern "C" int fp_bn_bwd(const void* dy, const void* y, const void* z, const flo
       static_cast<const uint4*>(dy), grad_dtype, relu ? static_cast<const uint4*>(y) : nullptr,
       static_cast<const uint4*>(z), act_dtype, save_mean, save_invstd, M, C, workspace);
   FP_CHECK_LAUNCH("fp_bn_bwd(reduce)");
-  partial_sum_kernel<<<nblocks(static_cast<long long>(C) * 32, 256), 256, 0, st>>>(workspace, nblk, C, dbeta, dgamma);
+  partial_sum_kernel<<<C, SUM_THREADS, 0, st>>>(workspace, nblk, C, dbeta, dgamma);
   FP_CHECK_LAUNCH("fp_bn_bwd(sum)");
   const long long n8 = M * (C / 8);
   bn_bwd_apply_kernel<<<nblocks(n8, 256), 256, 0, st>>>(
@@ -731,7 +735,7 @@ extern "C" int fp_bias_grad(const void* dz, long long M, int C, int grad_dtype, 
   col_reduce_kernel<2><<<nblk, RED_THREADS, rows_per_pass * 2 * C * sizeof(float), st>>>(
       static_cast<const uint4*>(dz), grad_dtype, nullptr, nullptr, grad_dtype, nullptr, nullptr, M, C, workspace);
   FP_CHECK_LAUNCH("fp_bias_grad(reduce)");
-  partial_sum_kernel<<<nblocks(static_cast<long long>(C) * 32, 256), 256, 0, st>>>(workspace, nblk, C, dbias, nullptr);
+  partial_sum_kernel<<<C, SUM_THREADS, 0, st>>>(workspace, nblk, C, dbias, nullptr);
   FP_CHECK_LAUNCH("fp_bias_grad(sum)");
   return FP_OK;
 }

@@ -23,6 +23,7 @@ spike clips element-wise instead of turning into inf - inf = NaN downstream.  Ev
 tensor and the fp32 parameter gradients are un-scaled exactly (power of two) by the optimiser / the autograd glue.  ``bf16`` (scale 1) remains selectable.  Parameter gradients are fp32.
 """
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
@@ -47,6 +48,15 @@ class TrainEngine(Engine):
         self._red_ws = None
         self._wg_ws = None
         self._loss_ws = None
+        self.head_tensor_cores_wgrad = True      # measured: the tiled CUDA-core head wgrad (0.64 ms for head4) is no faster than the tensor-core one (0.55)
+        self._head_ws = None
+        # weight / bias gradients run on a second stream beside the data-gradient chain that is the backward's critical
+        # path (both only consume dZ): the many small latency-bound kernels (split-K reduces, bias column sums, head
+        # weight gradients) and the tails of the persistent convolution kernels back-fill each other
+        self.overlap_wgrad = os.environ.get('FP_OVERLAP_WGRAD', '1') != '0'
+        self._side = None
+        self._side_keep = []
+        self._red_ws_side = None
         self.grad_views = None      # optional {parameter: fp32 view} — gradients are written there (Trainer's flat buffer)
 
     def _gout(self, param, shape=None):
@@ -405,7 +415,37 @@ class TrainEngine(Engine):
         return outputs, (sv if save else None)
 
     # ------------------------------------------------------------------------------ backward pieces
+    def _on_side(self, fn, *keep):
+        """Run fn(stream_ptr) on the side stream, ordered after everything enqueued on the current stream so far; `keep`
+        are the tensors it reads (held until backward() joins the streams: the main stream's allocator must not reuse them
+        while the side stream still reads)."""
+        if not self.overlap_wgrad:
+            return fn(self._stream())
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        self._side_keep.extend(t for t in keep if t is not None)
+        with torch.cuda.stream(self._side):
+            fn(ctypes.c_void_p(self._side.cuda_stream))
+
+    def _join_side(self):
+        if self._side is not None and self.overlap_wgrad:
+            torch.cuda.current_stream().wait_stream(self._side)
+        self._side_keep.clear()
+
     def _wgrad(self, L, src0, src1, dz, grads, stream):
+        """dW (and db) of one convolution (on the side stream, see _on_side)."""
+        self._on_side(lambda st: self._wgrad_now(L, src0, src1, dz, grads, st), src0, src1, dz)
+
+    def _reduce_ws_for(self, stream):
+        if self._side is None or stream.value != self._side.cuda_stream:
+            return self._reduce_ws()
+        if self._red_ws_side is None:
+            self._red_ws_side = torch.empty_like(self._reduce_ws())
+        return self._red_ws_side
+
+    def _wgrad_now(self, L, src0, src1, dz, grads, stream):
         """dW (and db) of one convolution from its gathered input and dZ [B][ho][wo][ld]."""
         b, ho, wo, ld = dz.shape
         d = self._desc(L, src0, src1, ho, wo)
@@ -422,10 +462,10 @@ class TrainEngine(Engine):
         if L.bias is not None:
             if ld == L.cout:
                 db = self._gout(L.bias)
-                _lib.check(self.lib.fp_bias_grad(_ptr(dz), b * ho * wo, ld, self.gfmt, _ptr(db), _ptr(self._reduce_ws()), stream))
+                _lib.check(self.lib.fp_bias_grad(_ptr(dz), b * ho * wo, ld, self.gfmt, _ptr(db), _ptr(self._reduce_ws_for(stream)), stream))
             else:       # heads: dZ rows are padded to 8 channels, the bias has 2
                 tmp = torch.empty(ld, dtype=torch.float32, device=dz.device)
-                _lib.check(self.lib.fp_bias_grad(_ptr(dz), b * ho * wo, ld, self.gfmt, _ptr(tmp), _ptr(self._reduce_ws()), stream))
+                _lib.check(self.lib.fp_bias_grad(_ptr(dz), b * ho * wo, ld, self.gfmt, _ptr(tmp), _ptr(self._reduce_ws_for(stream)), stream))
                 db = self._gout(L.bias)
                 db.copy_(tmp[:L.cout])
             self.launches += 2
@@ -542,10 +582,26 @@ class TrainEngine(Engine):
                 return self._dgrad_full(L, dz, stream)
 
             def head_bwd(L, src, dzh, dst, accumulate):
-                """weight/bias gradient of a head (tensor-core wgrad: faster than the CUDA-core fp_head_conv_wgrad at
-                these sizes) and its data gradient (CUDA-core kernel: reflect adjoint + ELU' of src fused) into dst."""
+                """weight/bias gradient of a head (tiled CUDA-core kernel: N = 2 would waste 126 of the tensor-core
+                kernel's 128 accumulator rows at the cost of a full 32-channel layer) and its data gradient (CUDA-core
+                kernel: reflect adjoint + ELU' of src fused) into dst."""
                 bb, hh_, ww_, cc_ = src.shape
-                self._wgrad(L, src, None, dzh, grads, stream)
+                if self.head_tensor_cores_wgrad:
+                    self._wgrad(L, src, None, dzh, grads, stream)
+                else:
+                    need = lib.fp_head_conv_wgrad_workspace_floats(cc_)
+                    if self._head_ws is None or self._head_ws.numel() < need:
+                        self._head_ws = torch.empty(need, dtype=torch.float32, device=src.device)
+                    dw, db = self._gout(L.weight), self._gout(L.bias)
+
+                    def run(st, L=L, src=src, dzh=dzh, dw=dw, db=db):
+                        self._prof('wgrad', L, bb * hh_ * ww_)
+                        _lib.check(lib.fp_head_conv_wgrad(_ptr(src), _ptr(dzh), bb, hh_, ww_, cc_, self.fmt, self.gfmt, 0,
+                                                          _ptr(dw), _ptr(db), _ptr(self._head_ws), st))
+                        self._prof_end()
+                    self._on_side(run, src, dzh)
+                    self.launches += 2
+                    grads[L.weight], grads[L.bias] = dw, db
                 _lib.check(lib.fp_head_conv_dgrad(_ptr(dzh), _ptr(L.weight.detach()), bb, hh_, ww_, cc_, 1 if accumulate else 0,
                                                   _ptr(src), FP_ACT_ELU, self.fmt, self.gfmt, _ptr(dst), stream))
                 self.launches += 1
@@ -643,4 +699,5 @@ class TrainEngine(Engine):
         stem = self.layers['stem']
         dz0, _ = self._bn_bwd(sv, stem, dfeat[0], True, False, grads, stream)
         self._wgrad(stem, sv['s2d'], None, dz0, grads, stream)
+        self._join_side()
         return grads

@@ -14,6 +14,7 @@ tg = {k: v for k, v in data.items() if k != 'image'}
 for _ in range(3):
     tr.step(data['image'], tg)
 tr.eng.profile = []
+tr.eng.overlap_wgrad = False      # serialise the launches: per-kernel CUDA-event times
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 e0.record(); tr.step(data['image'], tg); e1.record(); torch.cuda.synchronize()
 prof = tr.eng.profile; tr.eng.profile = None

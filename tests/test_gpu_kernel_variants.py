@@ -51,6 +51,9 @@ def P(t):
     dict(c0=64, c1=0, up0=0, pad=1, pad_mode=0, cout=64, h=12, w=160, b=2),     # 48x160-class layer (Wo = 160: 62.5 % of 2 segments)
     dict(c0=128, c1=0, up0=0, pad=1, pad_mode=1, cout=64, h=6, w=80, b=2),      # 24x80-class layer, 2 channel blocks
     dict(c0=64, c1=0, up0=0, pad=2, pad_mode=0, cout=64, h=12, w=160, b=2),     # its data gradient (Wo = 162)
+    dict(c0=64, c1=0, up0=0, pad=1, pad_mode=1, cout=64, h=9, w=128, b=1),      # 3 items: an unpaired last item (cp.async strips)
+    dict(c0=32, c1=0, up0=0, pad=2, pad_mode=0, cout=32, h=18, w=100, b=1),     # 3 items, TMA strips
+    dict(c0=32, c1=0, up0=0, pad=1, pad_mode=1, cout=32, h=6, w=128, b=1),      # a single item (one CTA, partner missing)
 ])
 def test_rowstream_matches_strip_kernel_and_torch(cfg):
     lib = _lib.load()

@@ -22,10 +22,21 @@ def _storage_type(request):
     BF, DT = (1, torch.bfloat16) if request.param == 'bf16' else (0, torch.float16)
     yield
     BF, DT = 1, torch.bfloat16
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
+_KEEP = []
 
 
 def P(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    """Device pointer of `t`.  The tensor is kept alive until the test ends: the launches are asynchronous, and a
+    temporary such as ``nhwc(x)`` would otherwise be freed -- and its block handed to the next temporary -- while a
+    kernel still reads it."""
+    if t is None:
+        return None
+    _KEEP.append(t)
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def nhwc(t):          # NCHW fp32 -> NHWC bf16
