@@ -538,7 +538,8 @@ class TrainEngine(Engine):
         return dz, g
 
     # ------------------------------------------------------------------------------ backward
-    def backward(self, douts, sv):
+    def backward(self, douts, sv, on_decoders_done=None):       # on_decoders_done(side_stream, tag): tag 4 = both decoders,
+        #                                                              3 = encoder layer4, 2 = layer3 finished their gradients
         """douts: {'1/8','1/4','1/2','1/1'} -> d(loss)/d(output) fp32 [B,4,H,W].  Returns {parameter: fp32 grad}; the
         gradients are multiplied by ``self.grad_scale`` (the loss scale; a power of two) -- the caller divides it out."""
         if sv is None:
@@ -668,6 +669,10 @@ class TrainEngine(Engine):
                         self._fold(dvp, hh // 2, ww // 2, 0, x.shape[3], False, dfeat[4], True, None, FP_ACT_NONE, stream)
                 del dvp
 
+        if on_decoders_done is not None:
+            # every decoder parameter gradient has been enqueued (weight gradients on the side stream): the data-parallel
+            # trainer starts all-reducing that bucket while the encoder's backward runs
+            on_decoders_done(self._side if self.overlap_wgrad else None, 4)
         # ---- encoder, last block first.  dy = gradient of the current block's output.
         dy = dfeat[4]
         for idx in range(len(self.enc_blocks) - 1, -1, -1):
@@ -690,6 +695,8 @@ class TrainEngine(Engine):
                 dres = g
             dy = self._dgrad_plain(c1, dz1, (x_in.shape[1], x_in.shape[2]), dres, stream)
             del dz2, g, dt1, dz1
+            if first_of_stage and on_decoders_done is not None and li >= 2:
+                on_decoders_done(self._side if self.overlap_wgrad else None, li)     # layer4 (li 3) / layer3 (li 2) are done
         # dy is now the gradient of the max-pool output; f0 also received gradient from the decoders
         f0 = feats[0]
         if dfeat[0] is None:

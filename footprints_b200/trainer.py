@@ -11,6 +11,7 @@ BatchNorm2d).  Parameters are re-pointed into one flat fp32 buffer so that the a
 launches; ``net.state_dict()`` keeps working (the parameters are views).
 """
 import ctypes
+import os
 
 import torch
 
@@ -67,8 +68,28 @@ class Trainer:
                 p.data = v
                 views[p] = self.grad[o:o + p.numel()].view(p.shape)
         self.eng.grad_views = views
+        # gradient buckets in the order the backward finishes them: decoders (the flat buffer's tail), encoder layer4,
+        # layer3, then the rest (layer2, layer1, stem).  bounds[tag] = first flat element of that bucket.
+        first = {}
+        for L, o in self._layer_offsets(offs):
+            tag = 4 if not L.name.startswith(('stem', 'enc')) else (3 if L.name.startswith('enc4') else
+                                                                  (2 if L.name.startswith('enc3') else 0))
+            first.setdefault(tag, o)
+        self._bucket = {4: (first[4], total), 3: (first[3], first[4]), 2: (first[2], first[3])}
+        self._rest_end = first[2]
+        self._comm_stream = None
         self.step_count = 0
         self.lib = _lib.load()
+
+    def _layer_offsets(self, offs):
+        """(layer, flat offset of its first parameter) in the flat buffer's order."""
+        i = 0
+        for L in self.eng.layers.values():
+            n = sum(1 for p in (L.weight, L.bias, L.bn.weight if L.bn is not None else None,
+                                L.bn.bias if L.bn is not None else None) if p is not None)
+            if i < len(offs):
+                yield L, offs[i]
+            i += n
 
     def _hyper(self, name, default):
         return self.optimiser.param_groups[0][name] if self.optimiser is not None else default
@@ -134,12 +155,46 @@ class Trainer:
         outs, saved = self.eng.forward_train(image)
         losses21, grads = fused_loss([outs[k] for k in SCALES], targets, self.depth_range, self.prior, True)
         self.eng.launches += 2
-        self.eng.backward(dict(zip(SCALES, grads)), saved)
+        self._pending = []
+        hook = self._reduce_decoder_bucket if (self.world > 1 and self.bucketed and not torch.cuda.is_current_stream_capturing()) else None
+        self.eng.backward(dict(zip(SCALES, grads)), saved, on_decoders_done=hook)
         del saved, grads, outs
         if adam_from_device is None:
             return losses21
         self._adam(adam_from_device)
         return losses21
+
+    # world > 1: all-reduce gradient buckets while the rest of the backward runs (FP_DP_BUCKETS=0: one all-reduce at the end)
+    bucketed = os.environ.get('FP_DP_BUCKETS', '1') != '0' 
+
+    def _reduce_decoder_bucket(self, side_stream, tag=4):
+        """Called by the backward when a bucket's gradients have all been enqueued (tag 4: both decoders, 3: encoder layer4,
+        2: layer3): all-reduce that slice of the flat gradient on a communication stream that waits for the main stream
+        and the weight-gradient side stream -- NOT the other way round, so the rest of the backward runs underneath."""
+        import torch.distributed as dist
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        cs = self._comm_stream
+        cs.wait_stream(torch.cuda.current_stream())
+        if side_stream is not None:
+            cs.wait_stream(side_stream)
+        with torch.cuda.stream(cs):
+            lo, hi = self._bucket[tag]
+            self._pending.append(dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def _finish_all_reduce(self):
+        """Sum the rest of the flat gradient over ranks (everything when no bucket went ahead) and join."""
+        import torch.distributed as dist
+        if self.world <= 1:
+            return
+        if self._pending:
+            dist.all_reduce(self.grad[:self._rest_end], op=dist.ReduceOp.SUM, group=self.pg)
+            for w in self._pending:
+                w.wait()                      # the current stream waits for the bucket's collective
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._pending = []
+        else:
+            self.sync.all_reduce_(self.grad)
 
     def _push_hyper(self):
         """Adam's per-step scalars -> device (pinned staging, async copy ordered before the kernel on this stream).  Both the
@@ -163,6 +218,12 @@ class Trainer:
         self.eng.launches += 1
 
     def enable_cuda_graph(self, enabled=True):
+        if self.world > 1:
+            # measured on 2 B200s: capturing the step while NCCL's process group is alive deadlocks (global and thread-local
+            # capture modes alike); data-parallel runs use the eager step with the bucketed all-reduce overlapping the
+            # backward (the step is GPU-bound: ~5 ms of host enqueue under ~35 ms of device time; the graph is worth
+            # ~0.5 ms)
+            enabled = False
         """Capture the step into a CUDA graph on the third call with a given input shape (the first two run eagerly: lazy
         allocations, function attributes) and replay it afterwards: ~450 kernel launches become one graph launch, so the
         host (ctypes calls, Python) is off the critical path.  Inputs are copied into static buffers before each replay;
@@ -209,13 +270,13 @@ class Trainer:
                 self._graph.replay()
                 self.eng.launches += self._graph_launches
                 if not self._graph_adam:
-                    self.sync.all_reduce_(self.grad)
+                    self._finish_all_reduce()
                     self._adam(False)
                 self.net._weights_epoch = getattr(self.net, '_weights_epoch', 0) + 1
                 return self._graph_out
             self._eager_calls += 1
         losses21 = self._step_body(image, targets, None)
-        self.sync.all_reduce_(self.grad)                                  # sum over ranks; Adam applies 1/world
+        self._finish_all_reduce()                                         # sum over ranks; Adam applies 1/world
         self.step_count += 1
         self._adam(False)
         self.net._weights_epoch = getattr(self.net, '_weights_epoch', 0) + 1     # eval engine must re-pack / re-fold
