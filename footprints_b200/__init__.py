@@ -7,5 +7,6 @@ Public surface mirrors the reference (nianticlabs/footprints): ``FootprintNetwor
 from .network import FootprintNetwork, FootprintsModel, ResnetEncoder, SkipDecoder  # noqa: F401
 from .model_manager import ModelManager  # noqa: F401
 from .losses import LossManager  # noqa: F401
+from .segmentor import Segmentor  # noqa: F401
 
-__all__ = ['FootprintNetwork', 'FootprintsModel', 'ResnetEncoder', 'SkipDecoder', 'ModelManager', 'LossManager']
+__all__ = ['FootprintNetwork', 'FootprintsModel', 'ResnetEncoder', 'SkipDecoder', 'ModelManager', 'LossManager', 'Segmentor']

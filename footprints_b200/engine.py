@@ -132,9 +132,13 @@ class Engine:
                 self.enc_blocks.append((li, c1, ds, c2))
                 cin = cout
         self.dec = {}
-        for dname, dec in (('mask', self.net.mask_decoder), ('depth', self.net.depth_decoder)):
+        # FootprintNetwork: two decoders with 2-channel heads; Segmentor (segmentor.py): ONE decoder, 1-channel heads
+        self.is_segmentor = hasattr(self.net, 'decoder')
+        decoders = (('seg', self.net.decoder),) if self.is_segmentor else \
+            (('mask', self.net.mask_decoder), ('depth', self.net.depth_decoder))
+        for dname, dec in decoders:
             d = {}
-            head_act = FP_ACT_SIGMOID if dec.apply_sigmoid else FP_ACT_NONE
+            head_act = FP_ACT_SIGMOID if getattr(dec, 'apply_sigmoid', False) else FP_ACT_NONE
             for bi, (ci, co) in enumerate(((512, 256), (256, 128), (128, 64), (64, 64)), start=1):
                 blk = getattr(dec, f'block{bi}')
                 pre, post = blk.pre_concat_conv, blk.post_concat_conv
@@ -284,7 +288,7 @@ class Engine:
         """OutConvBlock conv (+ sigmoid): footprints/network.py:174-178.  Default: the row-streaming tensor-core kernel
         with the two output channels padded to N = 16 (the tensor pipe is idle on these HBM-bound layers; one
         N = 48 instruction per input row, dx and K step); ``head_tensor_cores = False`` selects the CUDA-core kernels."""
-        if self.head_tensor_cores:
+        if self.head_tensor_cores or L.cout != 2:
             return self._conv(L, src, None, out, None, stream)
         b, h, w, c = src.shape
         _lib.check(self.lib.fp_head_conv_fwd(_ptr(src), _ptr(L.weight.detach()), _ptr(L.bias.detach()), b, h, w, c,
@@ -312,6 +316,8 @@ class Engine:
         lib = self.lib
 
         if self.precise:
+            if self.is_segmentor:
+                raise NotImplementedError('precise mode is implemented for FootprintNetwork')
             return self._forward_precise(image, stream)
         s2d = self._buf('s2d', (b, h // 2, w // 2, 16))
         _lib.check(lib.fp_stem_prep(_ptr(image), b, h, w, self.fmt, _ptr(s2d), stream))
@@ -338,7 +344,7 @@ class Engine:
         feats.append(x)
 
         heads = {}
-        for dname in ('mask', 'depth'):
+        for dname in self.dec:
             d = self.dec[dname]
             x = feats[4]
             for bi in range(1, 5):
@@ -354,7 +360,7 @@ class Engine:
                 x = self._buf(f'{dname}.b{bi}.post2', (b, 2 * hh, 2 * ww, co))
                 self._conv(d[f'b{bi}.post2'], t3, None, x, None, stream)
                 if bi >= 2:
-                    hd = self._buf(f'{dname}.head{bi - 1}', (b, 2 * hh, 2 * ww, 2), torch.float32)
+                    hd = self._buf(f'{dname}.head{bi - 1}', (b, 2 * hh, 2 * ww, d[f'head{bi - 1}'].cout), torch.float32)
                     self._head(d[f'head{bi - 1}'], x, hd, stream)
                     heads[(dname, bi - 1)] = hd
             hh, ww = x.shape[1], x.shape[2]
@@ -362,10 +368,14 @@ class Engine:
             self._conv(d['o4.c1'], x, None, t, None, stream)
             t2 = self._buf(f'{dname}.o4.c2', (b, 2 * hh, 2 * ww, 32))
             self._conv(d['o4.c2'], t, None, t2, None, stream)
-            hd = self._buf(f'{dname}.head4', (b, 2 * hh, 2 * ww, 2), torch.float32)
+            hd = self._buf(f'{dname}.head4', (b, 2 * hh, 2 * ww, d['head4'].cout), torch.float32)
             self._head(d['head4'], t2, hd, stream)
             heads[(dname, 4)] = hd
 
+        if self.is_segmentor:
+            # preprocessing/segmentation/network.py:83-101: a LIST of the four 1-channel maps at their own resolution
+            # ([B,h,w,1] NHWC is [B,1,h,w] NCHW); fresh tensors, the head buffers are reused by the next call
+            return [heads[('seg', i)].view(b, 1, heads[('seg', i)].shape[1], heads[('seg', i)].shape[2]).clone() for i in (1, 2, 3, 4)]
         return self._assemble(heads, b, h, w, image.device, stream)
 
     def _assemble(self, heads, b, h, w, dev, stream):

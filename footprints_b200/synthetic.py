@@ -91,7 +91,24 @@ def state_spec(arch='resnet34'):
     return spec
 
 
-def synthetic_state_dict(arch='resnet34', seed=0, trained_like=True):
+def segmentor_state_spec(arch='resnet34'):
+    """Ordered {key: shape} of the ground-segmentation network's ``state_dict`` (use_PSP=False):
+    footprints/preprocessing/segmentation/network.py:13-104 -- the same encoder, ONE skip decoder, 1-channel heads."""
+    spec = OrderedDict((k, v) for k, v in state_spec(arch).items() if k.startswith('encoder.'))
+    dec = 'decoder'
+    for bi, (ci, co) in enumerate(((512, 256), (256, 128), (128, 64), (64, 64)), start=1):
+        _conv_block_spec(f'{dec}.block{bi}.pre_concat_conv', ci, co, spec)
+        _conv_block_spec(f'{dec}.block{bi}.post_concat_conv', 2 * co, co, spec)
+    for oi, ci in ((1, 128), (2, 64), (3, 64)):
+        spec[f'{dec}.outconv{oi}.conv1.weight'] = (1, ci, 3, 3)
+        spec[f'{dec}.outconv{oi}.conv1.bias'] = (1,)
+    _conv_block_spec(f'{dec}.outconv4.0', 64, 32, spec)
+    spec[f'{dec}.outconv4.1.conv1.weight'] = (1, 32, 3, 3)
+    spec[f'{dec}.outconv4.1.conv1.bias'] = (1,)
+    return spec
+
+
+def synthetic_state_dict(arch='resnet34', seed=0, trained_like=True, spec=None):
     """Deterministic weights with non-trivial BatchNorm statistics.
 
     Encoder convs ~ N(0, 2/fan_out) (torchvision resnet.py kaiming fan_out init), decoder convs
@@ -100,7 +117,7 @@ def synthetic_state_dict(arch='resnet34', seed=0, trained_like=True):
     constructor defaults (1, 0, 0, 1)."""
     g = torch.Generator().manual_seed(seed)
     sd = OrderedDict()
-    for key, shape in state_spec(arch).items():
+    for key, shape in (spec if spec is not None else state_spec(arch)).items():
         leaf = key.rsplit('.', 1)[1]
         if leaf == 'num_batches_tracked':
             sd[key] = torch.zeros((), dtype=torch.long)

@@ -49,6 +49,7 @@ class TrainEngine(Engine):
         self._wg_ws = None
         self._loss_ws = None
         self.head_tensor_cores_wgrad = True      # measured: the tiled CUDA-core head wgrad (0.64 ms for head4) is no faster than the tensor-core one (0.55)
+        self.head_tensor_cores_dgrad = False     # measured: full correlation on the general kernel (K = 9 x 8) + fold: 0.71 + 0.25 ms for head4 vs 0.9 ms CUDA-core
         self._head_ws = None
         # weight / bias gradients run on a second stream beside the data-gradient chain that is the backward's critical
         # path (both only consume dZ): the many small latency-bound kernels (split-K reduces, bias column sums, head
@@ -127,8 +128,8 @@ class TrainEngine(Engine):
                                            7 if L.stem else L.k, 7 if L.stem else L.k, 16 if L.stem else cin, L.npad,
                                            L.kpad3, self.fmt, 2, 1 if L.stem else 0, first))
                 first += L.npad * L.kpad3
-            if L.is_head:
-                continue            # the heads' data gradient runs on the CUDA-core kernel (fp32 parameters)
+            # data-gradient operand (heads too: their data gradient is a K = 9 x 8 full correlation on the general tensor-core
+            # kernel followed by the usual fold -- half the time of the CUDA-core head kernel)
             # data-gradient operand: rows = cin, K = taps * cout_pad, filter rotated by 180 degrees
             if getattr(L, 'w_flip', None) is None:
                 L.cpad_out = max(8, L.cout)
@@ -603,6 +604,10 @@ class TrainEngine(Engine):
                     self._on_side(run, src, dzh)
                     self.launches += 2
                     grads[L.weight], grads[L.bias] = dw, db
+                if self.head_tensor_cores_dgrad:
+                    dvp = self._dgrad_full(L, dzh, stream)
+                    self._fold(dvp, hh_, ww_, 0, cc_, False, dst, accumulate, src, FP_ACT_ELU, stream)
+                    return
                 _lib.check(lib.fp_head_conv_dgrad(_ptr(dzh), _ptr(L.weight.detach()), bb, hh_, ww_, cc_, 1 if accumulate else 0,
                                                   _ptr(src), FP_ACT_ELU, self.fmt, self.gfmt, _ptr(dst), stream))
                 self.launches += 1

@@ -136,6 +136,29 @@ def network_forward(sd, image, arch='resnet34', training=False, new_stats=None, 
     return OrderedDict((k, torch.cat([mask[k], depth[k]], 1)) for k in mask)
 
 
+def segmentor_forward(sd, image, arch='resnet34', training=False):
+    """Segmentor.forward (use_PSP=False) -- footprints/preprocessing/segmentation/network.py:20-24,79-101: the same
+    encoder, one skip decoder, 1-channel heads (OutConvBlock :158-170: reflection pad + 3x3 conv, NO sigmoid, NO
+    upsampling).  Returns the list of four [B,1,h,w] outputs at 1/8, 1/4, 1/2 and full resolution."""
+    feats = encoder_forward(sd, image, arch, training)
+
+    def head(p, x):
+        return F.conv2d(F.pad(x, (1, 1, 1, 1), mode='reflect'), sd[f'{p}.conv1.weight'], sd[f'{p}.conv1.bias'])
+
+    outs = []
+    x = _up_block(sd, 'decoder.block1', feats[-1], feats[-2])
+    x = _up_block(sd, 'decoder.block2', x, feats[-3])
+    outs.append(head('decoder.outconv1', x))
+    x = _up_block(sd, 'decoder.block3', x, feats[-4])
+    outs.append(head('decoder.outconv2', x))
+    x = _up_block(sd, 'decoder.block4', x, feats[-5])
+    outs.append(head('decoder.outconv3', x))
+    x = F.interpolate(x, scale_factor=2, mode='nearest')
+    x = _conv_block(sd, 'decoder.outconv4.0', x)
+    outs.append(head('decoder.outconv4.1', x))
+    return outs
+
+
 def sigmoid_to_depth(s, min_depth=0.1, max_depth=100.0):
     """footprints/utils.py:36-42."""
     min_disp, max_disp = 1 / max_depth, 1 / min_depth

@@ -106,7 +106,40 @@ def run(arch, batch, height, width, tag):
           out['loss/loss'])
 
 
+def run_segmentor(batch, height, width, tag):
+    """Eval outputs of the reference's ground-segmentation network (preprocessing/segmentation/network.py, use_PSP=False)."""
+    from footprints_b200.synthetic import segmentor_state_spec
+    import footprints.preprocessing.segmentation.network as sn
+    sn.resnet34 = lambda pretrained=True: torchvision.models.resnet34(weights=None)
+    torch.manual_seed(0)
+    net = sn.Segmentor(pretrained=False, use_PSP=False)
+    spec = segmentor_state_spec('resnet34')
+    ref_sd = net.state_dict()
+    assert list(ref_sd.keys()) == list(spec.keys()), 'segmentor state_dict key order differs from reference'
+    for k in spec:
+        assert tuple(ref_sd[k].shape) == tuple(spec[k]), k
+    net.load_state_dict(synthetic_state_dict('resnet34', seed=0, spec=spec))
+    net.eval()
+    data = synthetic_batch(batch, height, width, seed=1)
+    with torch.no_grad():
+        outs = net(data['image'])
+    out = {}
+    for si, v in enumerate(outs):
+        idx = sample_idx(v.numel(), 300 + si).long()
+        out[f'eval/{si}/shape'] = np.array(v.shape)
+        out[f'eval/{si}/idx'] = idx.numpy().astype(np.int32)
+        out[f'eval/{si}/val'] = v.flatten()[idx].numpy()
+        out[f'eval/{si}/sum'] = np.float64(v.double().sum().item())
+    path = os.path.join(ROOT, 'tests', 'golden', f'{tag}.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, os.path.getsize(path), 'bytes')
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'segmentor':
+        run_segmentor(2, 64, 96, 'ref_segmentor_b2_64x96')
+        run_segmentor(1, 192, 640, 'ref_segmentor_b1_192x640')
+        sys.exit(0)
     run('resnet34', 2, 64, 96, 'ref_resnet34_b2_64x96')
     run('resnet18', 2, 64, 96, 'ref_resnet18_b2_64x96')
     run('resnet34', 1, 192, 640, 'ref_resnet34_b1_192x640')

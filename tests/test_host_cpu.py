@@ -91,3 +91,28 @@ def test_every_environment_switch_is_documented():
     doc = open(os.path.join(root, 'INTEGRATION.md')).read()
     missing = sorted(n for n in names if n not in doc)
     assert names and not missing, missing
+
+
+def test_segmentor_state_dict_and_random_init_match_reference():
+    """footprints_b200.Segmentor: same keys / shapes as the reference's segmentation network, and -- when the reference
+    checkout is present -- the same random-init weights for a given torch seed."""
+    from footprints_b200 import Segmentor
+    from footprints_b200.synthetic import segmentor_state_spec
+    net = Segmentor(pretrained=False)
+    sd, spec = net.state_dict(), segmentor_state_spec('resnet34')
+    assert list(sd.keys()) == list(spec.keys())
+    for k, shape in spec.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    if not os.path.isdir('/root/reference/footprints'):
+        return
+    import torchvision
+    sys.path.insert(0, '/root/reference')
+    import footprints.preprocessing.segmentation.network as sn
+    sn.resnet34 = lambda pretrained=True: torchvision.models.resnet34(weights=None)
+    torch.manual_seed(0)
+    ref = sn.Segmentor(pretrained=False).state_dict()
+    torch.manual_seed(0)
+    ours = Segmentor(pretrained=False).state_dict()
+    assert list(ref.keys()) == list(ours.keys())
+    for k in ref:
+        assert torch.equal(ref[k], ours[k]), k
