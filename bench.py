@@ -307,8 +307,7 @@ def main():
     # ---- roofline of the dominant kernel class (tcgen05 implicit-GEMM conv: forward + data-gradient launches)
     roofline = None
     # every rank runs the instrumented step (it contains the gradient all-reduce); only rank 0 records events
-    if rank == 0:
-        eng.profile = []
+    eng.profile = []          # on EVERY rank: an instrumented step runs eagerly (bucketed collectives), a graph replay does not
     overlap = getattr(eng, 'overlap_wgrad', False)
     if hasattr(eng, 'overlap_wgrad'):
         eng.overlap_wgrad = False          # per-launch CUDA-event times need the launches serialised on one stream
@@ -316,8 +315,8 @@ def main():
     torch.cuda.synchronize()
     if hasattr(eng, 'overlap_wgrad'):
         eng.overlap_wgrad = overlap
+    prof, eng.profile = eng.profile, None
     if rank == 0:
-        prof, eng.profile = eng.profile, None
         agg = {}
         for kind, name, flops, a, b, _ in prof:
             t, f, n = agg.get(kind, (0.0, 0.0, 0))

@@ -372,6 +372,11 @@ head_dgrad_kernel(const uint4* __restrict__ dz8 /*[B][H][W][8] 16-bit, ch 0..1 v
 constexpr int HD_SMEM_G = 9 * HT_ROWS * HT_COLS * static_cast<int>(sizeof(float2));     // 36 KB
 constexpr int HD_SMEM_DZ = (HT_ROWS + 2) * (HT_COLS + 2) * static_cast<int>(sizeof(float2));
 
+// HM = true (fp16 gradients): the FMA loop runs on packed half2 arithmetic -- the kernel is FMA-issue bound (18 terms per
+// output element; 22 % of the fp32 FMA peak with the scalar loop), HFMA2 halves the instruction count; the 18-term sums in
+// fp16 carry ~2e-3 relative error, the accuracy class of the 16-bit gradient tensors they are stored into.  G / dZ tiles
+// then hold {half2(gx, gx), half2(gy, gy)} and the weights {half2(w0[c], w0[c+1]), half2(w1[c], w1[c+1])} per channel pair.
+template <bool HM>
 __global__ void __launch_bounds__(HT_THREADS)
 head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ w, int H, int W, int C, int tiles_x,
                        int tiles_y, int accumulate, const uint4* __restrict__ yact, int act, int act_fmt, int grad_fmt,
@@ -386,9 +391,26 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
   const int ty0 = (bid % tiles_y) * HT_ROWS;
   const long long img = bid / tiles_y;
   const int c8 = C >> 3;
-  for (int i = tid; i < 9 * C; i += HT_THREADS) {
-    const int t = i / C, c = i - t * C;
-    sw[i] = make_float2(w[(0 * C + c) * 9 + t], w[(1 * C + c) * 9 + t]);
+  auto pack_g = [](float2 v) -> float2 {          // fp32 pair, or the two broadcast half2 registers of the packed loop
+    if (!HM) return v;
+    const __half2 a = __float2half2_rn(v.x), b = __float2half2_rn(v.y);
+    float2 o;
+    o.x = __uint_as_float(*reinterpret_cast<const uint32_t*>(&a));
+    o.y = __uint_as_float(*reinterpret_cast<const uint32_t*>(&b));
+    return o;
+  };
+  if (HM) {
+    for (int i = tid; i < 9 * (C >> 1); i += HT_THREADS) {
+      const int t = i / (C >> 1), c = (i - t * (C >> 1)) * 2;
+      const __half2 a = __floats2half2_rn(w[(0 * C + c) * 9 + t], w[(0 * C + c + 1) * 9 + t]);
+      const __half2 b = __floats2half2_rn(w[(1 * C + c) * 9 + t], w[(1 * C + c + 1) * 9 + t]);
+      sw[i] = make_float2(__uint_as_float(*reinterpret_cast<const uint32_t*>(&a)), __uint_as_float(*reinterpret_cast<const uint32_t*>(&b)));
+    }
+  } else {
+    for (int i = tid; i < 9 * C; i += HT_THREADS) {
+      const int t = i / C, c = i - t * C;
+      sw[i] = make_float2(w[(0 * C + c) * 9 + t], w[(1 * C + c) * 9 + t]);
+    }
   }
   // dZ halo tile (1 pixel each side, zero outside the image) staged once; every G term lies inside it
   for (int i = tid; i < (HT_ROWS + 2) * (HT_COLS + 2); i += HT_THREADS) {
@@ -429,13 +451,51 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
         }
       }
     }
-    G[i] = g;
+    G[i] = pack_g(g);
   }
   __syncthreads();
   const int lx = tid & 31, ly = (tid >> 5) * 4;
   const int px = tx0 + lx;
   for (int cb = 0; cb < C; cb += 16) {
     float acc[4][16];
+    if (HM) {
+      __half2 hacc[4][8];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hacc[r][i] = __float2half2_rn(0.f);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float2 g[4];
+        if (interior) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) g[r] = pack_g(dzs[(ly + r + 2 - t / 3) * (HT_COLS + 2) + lx + 2 - t % 3]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) g[r] = G[t * (HT_ROWS * HT_COLS) + (ly + r) * HT_COLS + lx];
+        }
+        const float2* wt = sw + t * (C >> 1) + (cb >> 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 ww = wt[i];
+          const uint32_t w0b = __float_as_uint(ww.x), w1b = __float_as_uint(ww.y);
+          const __half2 w0 = *reinterpret_cast<const __half2*>(&w0b), w1 = *reinterpret_cast<const __half2*>(&w1b);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const uint32_t gxb = __float_as_uint(g[r].x), gyb = __float_as_uint(g[r].y);
+            hacc[r][i] = __hfma2(w0, *reinterpret_cast<const __half2*>(&gxb),
+                                 __hfma2(w1, *reinterpret_cast<const __half2*>(&gyb), hacc[r][i]));
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 v = __half22float2(hacc[r][i]);
+          acc[r][2 * i] = v.x; acc[r][2 * i + 1] = v.y;
+        }
+    } else {
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -457,6 +517,7 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[r][i] = fmaf(ww.x, g[r].x, fmaf(ww.y, g[r].y, acc[r][i]));
       }
+    }
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -703,8 +764,10 @@ extern "C" int fp_head_conv_dgrad(const void* dz8, const float* w_oihw, int batc
   if (c % 16 == 0 && opts().head_tile != 0) {
     const int tiles_x = (w + HT_COLS - 1) / HT_COLS, tiles_y = (h + HT_ROWS - 1) / HT_ROWS;
     const int smem = HD_SMEM_G + HD_SMEM_DZ + 9 * c * static_cast<int>(sizeof(float2));
-    { const int arc = ensure_max_smem(reinterpret_cast<const void*>(head_dgrad_tile_kernel), HD_SMEM_G + HD_SMEM_DZ + 9 * HEAD_MAX_C * static_cast<int>(sizeof(float2)), "head_dgrad_tile_kernel"); if (arc != FP_OK) return arc; }
-    head_dgrad_tile_kernel<<<static_cast<unsigned>(static_cast<long long>(batch) * tiles_x * tiles_y), HT_THREADS, smem, st>>>(
+    const bool hm = grad_dtype == FP_F16 && opts().head_hmath != 0;
+    auto kern = hm ? head_dgrad_tile_kernel<true> : head_dgrad_tile_kernel<false>;
+    { const int arc = ensure_max_smem(reinterpret_cast<const void*>(kern), HD_SMEM_G + HD_SMEM_DZ + 9 * HEAD_MAX_C * static_cast<int>(sizeof(float2)), "head_dgrad_tile_kernel"); if (arc != FP_OK) return arc; }
+    kern<<<static_cast<unsigned>(static_cast<long long>(batch) * tiles_x * tiles_y), HT_THREADS, smem, st>>>(
         static_cast<const uint4*>(dz8), w_oihw, h, w, c, tiles_x, tiles_y, accumulate, static_cast<const uint4*>(y_act), act,
         act_dtype, grad_dtype, static_cast<uint4*>(dst));
   } else if (c == 32) {

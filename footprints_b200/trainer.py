@@ -218,17 +218,12 @@ class Trainer:
         self.eng.launches += 1
 
     def enable_cuda_graph(self, enabled=True):
-        if self.world > 1:
-            # measured on 2 B200s: capturing the step while NCCL's process group is alive deadlocks (global and thread-local
-            # capture modes alike); data-parallel runs use the eager step with the bucketed all-reduce overlapping the
-            # backward (the step is GPU-bound: ~5 ms of host enqueue under ~35 ms of device time; the graph is worth
-            # ~0.5 ms)
-            enabled = False
         """Capture the step into a CUDA graph on the third call with a given input shape (the first two run eagerly: lazy
         allocations, function attributes) and replay it afterwards: ~450 kernel launches become one graph launch, so the
         host (ctypes calls, Python) is off the critical path.  Inputs are copied into static buffers before each replay;
         Adam's per-step scalars live in device memory.  With world > 1 the graph ends after the backward and the NCCL
-        all-reduce + Adam follow eagerly."""
+        all-reduce + Adam follow eagerly (every rank must then take the same path on a given step: an eager step issues
+        four bucketed collectives, a replayed one a single collective)."""
         self._graph_on = enabled
         self._graph = None
         self._graph_key = None
@@ -244,7 +239,8 @@ class Trainer:
         l0 = self.eng.launches
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(g):
+        # world > 1: NCCL's watchdog thread polls CUDA events while this thread captures -> thread-local capture mode
+        with torch.cuda.graph(g, capture_error_mode='thread_local' if self.world > 1 else 'global'):
             out = self._step_body(self._static['image'], {k: self._static[k] for k in targets},
                                   True if in_graph_adam else None)
         self._graph, self._graph_out, self._graph_adam = g, out, in_graph_adam

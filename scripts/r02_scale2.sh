@@ -6,5 +6,5 @@ TAG=${1:-x}
 N=${2:-2}
 mkdir -p gpurun_out
 timeout 300 python bench.py --gpus 1 --no-cpu-baseline --no-precise > gpurun_out/${TAG}_n1.json 2> gpurun_out/${TAG}_n1.err; cut -c1-170 gpurun_out/${TAG}_n1.json
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --no-cpu-baseline --no-precise > gpurun_out/${TAG}_n${N}.json 2> gpurun_out/${TAG}_n${N}.err
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --no-cpu-baseline --no-precise > gpurun_out/${TAG}_n${N}.json 2> gpurun_out/${TAG}_n${N}.err
 grep -h '"metric"' gpurun_out/${TAG}_n${N}.json | cut -c1-170; tail -2 gpurun_out/${TAG}_n${N}.err
