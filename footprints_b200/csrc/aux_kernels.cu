@@ -407,6 +407,32 @@ extern "C" int fp_maxpool3x3s2_split(const void* in_hi, const void* in_lo, int b
   return FP_OK;
 }
 
+// Output edge of the batched test-set inference (footprints/evaluation/inference.py:104-108 + datasets/inference_dataset.py:35-39):
+// full-resolution prediction only, sigmoid on the two mask channels ("not applied in network for stability of BCE
+// loss"), stored as float16 -- what the reference computes with three extra passes (sigmoid in place, .cpu(), astype(np.float16))
+__global__ void heads_to_nchw_f16_post_kernel(const float2* __restrict__ mask_head, const float2* __restrict__ depth_head,
+                                              long long hw, long long n, __half* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  const long long b = idx / hw, pix = idx - b * hw;
+  const float2 m = mask_head[idx], d = depth_head[idx];
+  __half* o = out + b * 4 * hw + pix;
+  o[0] = __float2half_rn(1.f / (1.f + __expf(-m.x)));
+  o[hw] = __float2half_rn(1.f / (1.f + __expf(-m.y)));
+  o[2 * hw] = __float2half_rn(d.x);
+  o[3 * hw] = __float2half_rn(d.y);
+}
+
+extern "C" int fp_heads_to_nchw_f16_post(const float* mask_head, const float* depth_head, int batch, int h, int w, void* out_f16,
+                                         void* stream) {
+  if (!mask_head || !depth_head || !out_f16) return set_error(FP_ERR_ARG, "fp_heads_to_nchw_f16_post: null argument");
+  const long long hw = static_cast<long long>(h) * w, n = hw * batch;
+  heads_to_nchw_f16_post_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(mask_head), reinterpret_cast<const float2*>(depth_head), hw, n, static_cast<__half*>(out_f16));
+  FP_CHECK_LAUNCH("fp_heads_to_nchw_f16_post");
+  return FP_OK;
+}
+
 extern "C" int fp_heads_to_nchw(const float* mask_head, const float* depth_head, int batch, int h, int w, int scale,
                                 float* out, void* stream) {
   if (!mask_head || !depth_head || !out || scale < 1) return set_error(FP_ERR_ARG, "fp_heads_to_nchw: bad argument");

@@ -393,10 +393,9 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
   const int c8 = C >> 3;
   auto pack_g = [](float2 v) -> float2 {          // fp32 pair, or the two broadcast half2 registers of the packed loop
     if (!HM) return v;
-    const __half2 a = __float2half2_rn(v.x), b = __float2half2_rn(v.y);
-    float2 o;
-    o.x = __uint_as_float(*reinterpret_cast<const uint32_t*>(&a));
-    o.y = __uint_as_float(*reinterpret_cast<const uint32_t*>(&b));
+    float2 o;                                   // saturating: a sum of up to four saturated dZ values must not become inf
+    o.x = __uint_as_float(f32x2_to_f16x2_sat(v.x, v.x));
+    o.y = __uint_as_float(f32x2_to_f16x2_sat(v.y, v.y));
     return o;
   };
   if (HM) {
@@ -492,8 +491,9 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float2 v = __half22float2(hacc[r][i]);
-          acc[r][2 * i] = v.x; acc[r][2 * i + 1] = v.y;
+          const float2 v = __half22float2(hacc[r][i]);          // an overflowed sum (inf) clips like every other conversion
+          acc[r][2 * i] = fminf(fmaxf(v.x, -65504.f), 65504.f);
+          acc[r][2 * i + 1] = fminf(fmaxf(v.y, -65504.f), 65504.f);
         }
     } else {
 #pragma unroll

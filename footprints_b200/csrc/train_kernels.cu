@@ -443,6 +443,44 @@ __global__ void fold_kernel(const uint4* __restrict__ dvp, int Hv, int Wv, int c
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   constexpr int R = UP ? 2 : 1;
+  // interior fast path (all but the two rows / columns next to each border): every virtual pixel has exactly one padded
+  // source, no reflected terms -- straight-line loads, all of them in flight at once
+  const int vy0 = UP ? 2 * y : y, vx0 = UP ? 2 * x : x;
+  if (vy0 > 1 && vy0 + R - 1 < Hv - 2 && vx0 > 1 && vx0 + R - 1 < Wv - 2) {
+    uint4 v[R * R];
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+      for (int bb = 0; bb < R; ++bb)
+        v[a * R + bb] = dvp[((static_cast<long long>(b) * Hp + vy0 + a + 1) * Wp + vx0 + bb + 1) * ccat8 + coff8 + cc];
+    uint4 prev = make_uint4(0u, 0u, 0u, 0u), ya = make_uint4(0u, 0u, 0u, 0u);
+    if (accumulate) prev = dst[idx];
+    if (yact != nullptr) ya = yact[idx];
+#pragma unroll
+    for (int k = 0; k < R * R; ++k) {
+      float f[8];
+      unpack8(v[k], grad_fmt, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+    if (accumulate) {
+      float f[8];
+      unpack8(prev, grad_fmt, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+    if (yact != nullptr) {
+      float fy[8];
+      unpack8(ya, act_fmt, fy);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (act == FP_ACT_ELU) acc[i] *= fy[i] > 0.f ? 1.f : fy[i] + 1.f;
+        else if (act == FP_ACT_RELU) acc[i] = fy[i] > 0.f ? acc[i] : 0.f;
+      }
+    }
+    dst[idx] = pack8(acc, grad_fmt);
+    return;
+  }
 #pragma unroll
   for (int a = 0; a < R; ++a) {
     const int vy = UP ? 2 * y + a : y;

@@ -297,7 +297,7 @@ class Engine:
 
     # ------------------------------------------------------------------------------ forward (inference)
     @torch.no_grad()
-    def forward(self, image):
+    def forward(self, image, post=None):
         """Eval-mode forward (folded BatchNorm).  Matches FootprintNetwork.forward of the reference in
         ``model.eval()`` (footprints/network.py:21-30)."""
         if self.net.training:
@@ -318,7 +318,7 @@ class Engine:
         if self.precise:
             if self.is_segmentor:
                 raise NotImplementedError('precise mode is implemented for FootprintNetwork')
-            return self._forward_precise(image, stream)
+            return self._forward_precise(image, stream, post)
         s2d = self._buf('s2d', (b, h // 2, w // 2, 16))
         _lib.check(lib.fp_stem_prep(_ptr(image), b, h, w, self.fmt, _ptr(s2d), stream))
         f0 = self._buf('f0', (b, h // 2, w // 2, 64))
@@ -372,6 +372,12 @@ class Engine:
             self._head(d['head4'], t2, hd, stream)
             heads[(dname, 4)] = hd
 
+        if post == 'inference_f16':
+            # evaluation/inference.py:104-108 + inference_dataset.py:35-39 fused into the output kernel: only the full-resolution
+            # prediction, sigmoid on the mask channels, float16 -- half the D2H bytes of the fp32 '1/1' tensor, no three extra scales
+            out = torch.empty((b, 4, h, w), dtype=torch.float16, device=image.device)
+            _lib.check(lib.fp_heads_to_nchw_f16_post(_ptr(heads[('mask', 4)]), _ptr(heads[('depth', 4)]), b, h, w, _ptr(out), stream))
+            return out
         if self.is_segmentor:
             # preprocessing/segmentation/network.py:83-101: a LIST of the four 1-channel maps at their own resolution
             # ([B,h,w,1] NHWC is [B,1,h,w] NCHW); fresh tensors, the head buffers are reused by the next call
@@ -390,7 +396,7 @@ class Engine:
             outputs[key] = out
         return outputs
 
-    def _forward_precise(self, image, stream):
+    def _forward_precise(self, image, stream, post=None):
         """Eval forward with the PRECISE_PREFIXES layers in split precision; everything else as in forward()."""
         lib = self.lib
         b, _, h, w = image.shape
@@ -464,4 +470,8 @@ class Engine:
             hd = self._buf(f'{dname}.head4', (b, 2 * hh, 2 * ww, 2), torch.float32)
             self._head(d['head4'], t2, hd, stream)
             heads[(dname, 4)] = hd
+        if post == 'inference_f16':
+            out = torch.empty((b, 4, h, w), dtype=torch.float16, device=image.device)
+            _lib.check(lib.fp_heads_to_nchw_f16_post(_ptr(heads[('mask', 4)]), _ptr(heads[('depth', 4)]), b, h, w, _ptr(out), stream))
+            return out
         return self._assemble(heads, b, h, w, image.device, stream)

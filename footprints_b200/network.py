@@ -201,5 +201,17 @@ class FootprintNetwork(nn.Module):
         return self.engine().forward(input_image)
 
 
+    def predict_for_saving(self, input_image):
+        """Output edge of the reference's batched inference (footprints/evaluation/inference.py:104-108,
+        datasets/inference_dataset.py:35-39): the full-resolution prediction with the sigmoid applied to the two mask
+        channels, as float16 ``[B,4,H,W]`` -- ``preds[:, 0:2] = sigmoid(preds[:, 0:2]); preds.cpu().numpy().astype(np.float16)``
+        of the reference, fused into the kernel that writes the output (eval mode only)."""
+        if self.training:
+            raise RuntimeError('predict_for_saving is an inference call; use model.eval()')
+        if not input_image.is_cuda:
+            raise RuntimeError('footprints_b200.FootprintNetwork runs on a B200 only (no CPU fallback)')
+        return self.engine().forward(input_image, post='inference_f16')
+
+
 # BASELINE.json's north_star calls the class "FootprintsModel"; the reference symbol is FootprintNetwork.
 FootprintsModel = FootprintNetwork

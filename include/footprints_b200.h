@@ -150,6 +150,13 @@ int fp_maxpool3x3s2(const void* in, int batch, int h, int w, int c, int dtype, v
 int fp_heads_to_nchw(const float* mask_head, const float* depth_head, int batch, int h, int w, int scale,
                      float* out_nchw, void* stream);
 
+/* Output edge of the test-set inference (footprints/evaluation/inference.py:104-108 and
+ * datasets/inference_dataset.py:35-39): the two full-resolution [batch][h][w][2] fp32 head maps -> ONE float16 NCHW
+ * [batch][4][h][w] tensor with the sigmoid applied to the two mask channels -- exactly the array the reference saves with
+ * np.save after `preds[:, 0:2] = sigmoid(preds[:, 0:2])`, `.cpu().numpy()`, `.astype(np.float16)`. */
+int fp_heads_to_nchw_f16_post(const float* mask_head, const float* depth_head, int batch, int h, int w, void* out_f16,
+                              void* stream);
+
 /* Heads (OutConvBlock, network.py:161-183): 3x3 reflection-padded convolution Cin -> 2 (+ Sigmoid) on CUDA cores
  * (N = 2 wastes the tensor-core tile).  x: NHWC 16-bit [batch][h][w][c], c a multiple of 8 <= 128; w_oihw [2][c][3][3]
  * and bias [2] are the fp32 parameters themselves; out: fp32 [batch][h][w][2] (input of fp_heads_to_nchw). */

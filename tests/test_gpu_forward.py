@@ -258,3 +258,20 @@ def test_precise_mode_meets_1e_3_on_every_scale(trained_like, shape):
         err = (out[k].cpu() - ref[k]).abs().max().item()
         print(f'precise eval trained_like={trained_like} {shape} scale {k}: max abs err {err:.3e} (bar 1e-03)')
         assert err <= 1e-3, (k, err)
+
+
+def test_predict_for_saving_matches_reference_postprocessing():
+    """SURVEY §8 f3 (output edge): the reference's test-set inference takes pred['1/1'], applies the sigmoid to the two
+    mask channels, moves it to the host and saves it as float16 (evaluation/inference.py:104-108,
+    datasets/inference_dataset.py:35-39); `predict_for_saving` fuses that into the output kernel."""
+    net = _net('resnet34', 'fp16')
+    img = synthetic_batch(2, 64, 96, 9)['image'].cuda()
+    ref = net(img)['1/1'].clone()
+    ref[:, 0:2] = torch.sigmoid(ref[:, 0:2])
+    ref16 = ref.cpu().numpy().astype(np.float16)
+    got = net.predict_for_saving(img)
+    assert got.dtype == torch.float16 and tuple(got.shape) == (2, 4, 64, 96)
+    diff = np.abs(got.cpu().numpy().astype(np.float32) - ref16.astype(np.float32)).max()
+    assert diff <= 1e-3, diff                      # one fp16 ulp near 1.0 (sigmoid via __expf vs torch's)
+    with pytest.raises(RuntimeError):
+        net.train().predict_for_saving(img)
