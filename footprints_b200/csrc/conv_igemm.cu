@@ -21,8 +21,11 @@
 //                                   segments are real pixels): one staged 130-pixel input row segment per (dy, channel
 //                                   block) serves the three dx taps through shifted UMMA descriptors; strips by TMA
 //                                   for zero-padded single-source inputs; the filter resident in shared memory.
-// What bounds them on the thin high-resolution layers: L2->SM operand bandwidth (~20 B/clk/SM) and
-// UMMA's max(M, N)/2-cycle cost per K = 16 step -- not HBM.
+//   conv_rowstream_kernel<BN,CB>    3x3 stride-1, Cout <= 64, rows >= 80 pixels: the default for the thin high-resolution
+//                                   layers (documented at the kernel).
+// What bounds them (measured): the deep layers L2->SM operand bandwidth (~50 B/clk/SM against the 94 B/clk a
+// 128x256 tile consumes at the tensor pipe's rate); the thin layers the epilogue's instruction stream -- neither HBM (DRAM
+// traffic = algorithmic bytes, 18-39 % busy) nor the tensor pipe (14-49 %).
 #include "fp_ptx.cuh"
 #include "fp_internal.h"
 #include "igemm_common.cuh"
@@ -870,8 +873,9 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
 }
 
 // ==================================================================================================
-// Row-streaming variant of the strip kernel  (EXPERIMENTAL: opt-in with FP_ROWSTREAM=1, not yet validated on a GPU --
-// written at the end of round 1 after the GPU budget was spent; the default dispatch never reaches it).
+// Row-streaming 3x3 convolution: the DEFAULT for Cout <= 64 on rows of >= 80 pixels (every 48x160 / 96x320 / 192x640
+// layer, forward and data gradient, and the 2-channel heads with N padded to 16); FP_ROWSTREAM=0 falls back to the strip
+// kernel.  Validated on B200 against the strip kernel and torch (tests/test_gpu_kernel_variants.py).
 //
 // Why: on the thin layers (Cout <= 64) a tcgen05.mma costs max(M, N)/2 = 64 cycles whatever N is, and L2->SM bandwidth
 // caps the strip fills; the strip kernel stages every input row three times (once per output row that uses it) and
@@ -880,8 +884,8 @@ conv_igemm_strip_kernel(const __grid_constant__ StripParams sp, const __grid_con
 // rows it feeds -- the B operand is [W(dy=0,dx) | W(dy=1,dx) | W(dy=2,dx)] (resident, stored in that order) and the
 // three accumulators are adjacent TMEM column blocks ordered by DEcreasing output row.  TMEM (512 columns) is split
 // in two halves of H = 256/BN row slots; a work item is H consecutive output rows of one column (H + 2 input rows,
-// i.e. 1.25x (BN=32) / 1.5x (BN=64) fills per output row instead of 3x, and 3x fewer instructions), items alternate
-// halves so that the epilogue of one item overlaps the MMAs of the next.
+// i.e. 1.25x (BN=32) / 1.5x (BN=64) fills per output row instead of 3x, and 3x fewer instructions).  A CTA works on a
+// PAIR of items at a time, one per TMEM half, each with its own MMA-issuing warp and two epilogue groups (see below).
 //   input row j of an item (virtual row v = yc - pad_t + j, j = 0 .. H+1) feeds output rows y = yc + j - dy:
 //   dy in [max(0, j-H+1), min(2, j)];  slot(y) = H-1-(y-yc)  (so dy = 0,1,2 are increasing columns).
 //   The first instruction touching a row slot (dy = 0 block, cb = dx = k = 0) is issued alone with accumulate = 0.

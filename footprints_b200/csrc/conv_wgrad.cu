@@ -449,9 +449,9 @@ conv_wgrad_strip_kernel(const __grid_constant__ WgradStripParams p, const __grid
 }
 
 // ==================================================================================================
-// Rolling, row-paired variant  (EXPERIMENTAL: opt-in with FP_WGRAD_ROLL=1, written after round 1's GPU budget was
-// spent, never run on hardware; the default dispatch does not reach it.  Control logic pinned on the CPU by
-// tests/test_wgrad_roll_emulation.py.)
+// Rolling, row-paired variant: the DEFAULT weight gradient for Cout <= 64 on strip-eligible layers (FP_WGRAD_ROLL=0 falls
+// back to the strip kernel above).  Validated on B200 against the strip kernel and autograd
+// (tests/test_gpu_kernel_variants.py); 58-61 % tensor-pipe active for 64-channel blocks (profiles/r02A_ncu_full_table.md).
 //
 // For Cout <= 64 the strip kernel above wastes half of every instruction's M = 128 and stages each input row and each dZ
 // row three times (once per filter row).  Here a CTA walks DOWN a column of row segments of one image: every input row
