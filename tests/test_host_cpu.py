@@ -116,3 +116,45 @@ def test_segmentor_state_dict_and_random_init_match_reference():
     assert list(ref.keys()) == list(ours.keys())
     for k in ref:
         assert torch.equal(ref[k], ours[k]), k
+
+
+def test_gradient_buckets_partition_the_flat_buffer_in_backward_order():
+    """Trainer's all-reduce buckets: decoders | encoder layer4 | layer3 | the rest, contiguous slices of the
+    flat gradient that cover it exactly once, in the order the backward finishes them."""
+    from footprints_b200.trainer import Trainer, trainable_parameters
+    net = FootprintNetwork(pretrained=False).train()
+    tr = Trainer(net)
+    total = tr.grad.numel()
+    (d0, d1), (a0, a1), (b0, b1) = tr._bucket[4], tr._bucket[3], tr._bucket[2]
+    assert d1 == total and a1 == d0 and b1 == a0 and 0 < tr._rest_end == b0
+    names = {id(p): n for n, p in net.named_parameters()}
+    where = {}
+    for p, o in zip(tr.params, tr._offs):
+        where[names[id(p)]] = o
+    for n, o in where.items():
+        if n.startswith(('mask_decoder', 'depth_decoder')):
+            assert d0 <= o < d1, n
+        elif n.startswith('encoder.layer4'):
+            assert a0 <= o < a1, n
+        elif n.startswith('encoder.layer3'):
+            assert b0 <= o < b1, n
+        else:
+            assert o < b0, n
+    assert len(tr.params) == len(trainable_parameters(net)) == len([p for p in net.parameters()]) - 72   # unused decoder BNs
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm): one JSON line, CPU only, unmodified reference modules
+    when baseline/_ref (or /root/reference) is importable."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--cpu-batch', '1',
+                          '--hw', '64x96'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'cpu_baseline', 'e2e'):
+        assert k in line, k
+    assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] in ('reference', 'port')
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
