@@ -55,6 +55,9 @@ PROTOTYPES = {
     'fp_maxpool3x3s2': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_heads_to_nchw': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_heads_to_nchw_f16_post': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    'fp_psp_fwd': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'fp_resize_u8_horizontal': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    'fp_resize_u8_vertical_to_f32': (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
     'fp_head_conv_fwd': (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'fp_head_conv_dgrad': (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp]),
     'fp_head_conv_wgrad_workspace_floats': (ctypes.c_longlong, [_i32]),

@@ -442,3 +442,93 @@ extern "C" int fp_heads_to_nchw(const float* mask_head, const float* depth_head,
   FP_CHECK_LAUNCH("fp_heads_to_nchw");
   return FP_OK;
 }
+
+// ---------------------------------------------------------------------------------- pyramid pooling (Segmentor, use_PSP=True)
+// preprocessing/segmentation/network.py:174-207: for s in (1, 2, 4, 6): AdaptiveAvgPool2d(s) -> 1x1 conv 512 -> 128 (no
+// bias) -> bilinear upsample back to h x w (align_corners=True); output = cat([x, x6, x4, x2, x1], channels).  One CTA per
+// (pyramid level, image): pooled cells and their 128-channel reductions live in shared memory, so the block reads x once and
+// writes the 1024-channel NHWC tensor the first decoder convolution consumes (the concat is a channel offset).
+namespace fp {
+namespace {
+constexpr int kPspC = 512, kPspR = 128, kPspThreads = 256;
+
+__global__ void __launch_bounds__(kPspThreads) psp_kernel(const uint16_t* __restrict__ x, int h, int w, int fmt,
+                                                         const float* __restrict__ w1, const float* __restrict__ w2,
+                                                         const float* __restrict__ w4, const float* __restrict__ w6,
+                                                         uint16_t* __restrict__ out) {
+  extern __shared__ float s_psp[];
+  const int level = blockIdx.x, b = blockIdx.y;              // level 0..3 -> pool 6, 4, 2, 1 (the order of the concat)
+  const int s = level == 0 ? 6 : (level == 1 ? 4 : (level == 2 ? 2 : 1));
+  const float* __restrict__ wr = level == 0 ? w6 : (level == 1 ? w4 : (level == 2 ? w2 : w1));
+  float* pooled = s_psp;                                     // [s*s][512]
+  float* reduced = s_psp + 36 * kPspC;                       // [s*s][128]
+  const uint16_t* xb = x + static_cast<long long>(b) * h * w * kPspC;
+  uint16_t* ob = out + static_cast<long long>(b) * h * w * (2 * kPspC);
+  const int tid = threadIdx.x;
+
+  // x itself -> channels [0, 512): this CTA copies its quarter (128 channels = 16 vectors of 8 per pixel)
+  for (int i = tid; i < h * w * 16; i += kPspThreads) {
+    const int pix = i >> 4, v = i & 15;
+    reinterpret_cast<uint4*>(ob + static_cast<long long>(pix) * (2 * kPspC) + level * 128)[v] =
+        __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(pix) * kPspC + level * 128) + v);
+  }
+  // adaptive average pooling: cell (i, j) covers rows [floor(i*h/s), ceil((i+1)*h/s)), columns likewise
+  for (int cell = 0; cell < s * s; ++cell) {
+    const int ci = cell / s, cj = cell - ci * s;
+    const int y0 = (ci * h) / s, y1 = ((ci + 1) * h + s - 1) / s;
+    const int x0 = (cj * w) / s, x1 = ((cj + 1) * w + s - 1) / s;
+    const float inv = 1.f / static_cast<float>((y1 - y0) * (x1 - x0));
+    for (int c = tid; c < kPspC; c += kPspThreads) {
+      float acc = 0.f;
+      for (int yy = y0; yy < y1; ++yy)
+        for (int xx = x0; xx < x1; ++xx) acc += from16(xb[(static_cast<long long>(yy) * w + xx) * kPspC + c], fmt);
+      pooled[cell * kPspC + c] = acc * inv;
+    }
+  }
+  __syncthreads();
+  // 1x1 convolution 512 -> 128 on the pooled cells: one warp per output channel, lanes split the input channels
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int co = warp; co < kPspR; co += kPspThreads / 32) {
+    float wv[kPspC / 32];
+#pragma unroll
+    for (int k = 0; k < kPspC / 32; ++k) wv[k] = __ldg(wr + co * kPspC + lane + 32 * k);
+    for (int cell = 0; cell < s * s; ++cell) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < kPspC / 32; ++k) acc += wv[k] * pooled[cell * kPspC + lane + 32 * k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) reduced[cell * kPspR + co] = acc;
+    }
+  }
+  __syncthreads();
+  // bilinear upsample s x s -> h x w, align_corners=True: src = dst * (s - 1) / (out - 1)
+  const float sy = h > 1 ? static_cast<float>(s - 1) / static_cast<float>(h - 1) : 0.f;
+  const float sx = w > 1 ? static_cast<float>(s - 1) / static_cast<float>(w - 1) : 0.f;
+  for (int i = tid; i < h * w * kPspR; i += kPspThreads) {
+    const int pix = i >> 7, co = i & (kPspR - 1);
+    const int yy = pix / w, xx = pix - yy * w;
+    const float fy = sy * yy, fx = sx * xx;
+    const int iy0 = static_cast<int>(fy), ix0 = static_cast<int>(fx);
+    const int iy1 = iy0 + (iy0 < s - 1 ? 1 : 0), ix1 = ix0 + (ix0 < s - 1 ? 1 : 0);
+    const float ly1 = fy - iy0, lx1 = fx - ix0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float v = ly0 * (lx0 * reduced[(iy0 * s + ix0) * kPspR + co] + lx1 * reduced[(iy0 * s + ix1) * kPspR + co]) +
+                    ly1 * (lx0 * reduced[(iy1 * s + ix0) * kPspR + co] + lx1 * reduced[(iy1 * s + ix1) * kPspR + co]);
+    ob[static_cast<long long>(pix) * (2 * kPspC) + kPspC + level * kPspR + co] = to16(v, fmt);
+  }
+}
+}  // namespace
+}  // namespace fp
+
+extern "C" int fp_psp_fwd(const void* x, int batch, int h, int w, int dtype, const float* w_pool1, const float* w_pool2,
+                          const float* w_pool4, const float* w_pool6, void* out, void* stream) {
+  if (!x || !w_pool1 || !w_pool2 || !w_pool4 || !w_pool6 || !out) return fp::set_error(FP_ERR_ARG, "fp_psp_fwd: null argument");
+  if (batch < 1 || batch > 65535 || h < 1 || w < 1) return fp::set_error(FP_ERR_ARG, "fp_psp_fwd: bad geometry %dx%dx%d", batch, h, w);
+  const int smem = (36 * fp::kPspC + 36 * fp::kPspR) * 4;
+  int rc = fp::ensure_max_smem(reinterpret_cast<const void*>(fp::psp_kernel), smem, "psp_kernel");
+  if (rc) return rc;
+  fp::psp_kernel<<<dim3(4, batch), fp::kPspThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(x), h, w, dtype, w_pool1, w_pool2, w_pool4, w_pool6, static_cast<uint16_t*>(out));
+  FP_CHECK_LAUNCH("fp_psp_fwd");
+  return FP_OK;
+}

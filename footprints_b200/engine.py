@@ -139,7 +139,9 @@ class Engine:
         for dname, dec in decoders:
             d = {}
             head_act = FP_ACT_SIGMOID if getattr(dec, 'apply_sigmoid', False) else FP_ACT_NONE
-            for bi, (ci, co) in enumerate(((512, 256), (256, 128), (128, 64), (64, 64)), start=1):
+            # Segmentor(use_PSP=True): the pyramid-pooling block doubles the channels entering block1 (segmentation/network.py:62)
+            first_in = 1024 if getattr(dec, 'use_PSP', False) else 512
+            for bi, (ci, co) in enumerate(((first_in, 256), (256, 128), (128, 64), (64, 64)), start=1):
                 blk = getattr(dec, f'block{bi}')
                 pre, post = blk.pre_concat_conv, blk.post_concat_conv
                 p = f'{dname}.block{bi}'
@@ -347,6 +349,14 @@ class Engine:
         for dname in self.dec:
             d = self.dec[dname]
             x = feats[4]
+            if self.is_segmentor and self.net.decoder.use_PSP:
+                # segmentation/network.py:82-83,174-207: pool / reduce / upsample / concat of all four levels in one kernel
+                psp = self.net.decoder.PSP
+                wts = [getattr(psp, f'block{i}').reduce.weight.detach().float().contiguous() for i in (1, 2, 3, 4)]
+                xp = self._buf('seg.psp', (b, x.shape[1], x.shape[2], 1024))
+                _lib.check(lib.fp_psp_fwd(_ptr(x), b, x.shape[1], x.shape[2], self.fmt, _ptr(wts[0]), _ptr(wts[1]), _ptr(wts[2]),
+                                          _ptr(wts[3]), _ptr(xp), stream))
+                x = xp
             for bi in range(1, 5):
                 skip = feats[4 - bi]
                 hh, ww = x.shape[1], x.shape[2]

@@ -91,12 +91,16 @@ def state_spec(arch='resnet34'):
     return spec
 
 
-def segmentor_state_spec(arch='resnet34'):
-    """Ordered {key: shape} of the ground-segmentation network's ``state_dict`` (use_PSP=False):
-    footprints/preprocessing/segmentation/network.py:13-104 -- the same encoder, ONE skip decoder, 1-channel heads."""
+def segmentor_state_spec(arch='resnet34', use_PSP=False):
+    """Ordered {key: shape} of the ground-segmentation network's ``state_dict``:
+    footprints/preprocessing/segmentation/network.py:13-104 -- the same encoder, ONE skip decoder, 1-channel heads; with
+    ``use_PSP`` the four 1x1 reduce convolutions of the pyramid-pooling block (:174-207) in front of a 1024-channel block1."""
     spec = OrderedDict((k, v) for k, v in state_spec(arch).items() if k.startswith('encoder.'))
     dec = 'decoder'
-    for bi, (ci, co) in enumerate(((512, 256), (256, 128), (128, 64), (64, 64)), start=1):
+    if use_PSP:
+        for i in (1, 2, 3, 4):
+            spec[f'{dec}.PSP.block{i}.reduce.weight'] = (128, 512, 1, 1)
+    for bi, (ci, co) in enumerate(((1024 if use_PSP else 512, 256), (256, 128), (128, 64), (64, 64)), start=1):
         _conv_block_spec(f'{dec}.block{bi}.pre_concat_conv', ci, co, spec)
         _conv_block_spec(f'{dec}.block{bi}.post_concat_conv', 2 * co, co, spec)
     for oi, ci in ((1, 128), (2, 64), (3, 64)):

@@ -157,6 +157,27 @@ int fp_heads_to_nchw(const float* mask_head, const float* depth_head, int batch,
 int fp_heads_to_nchw_f16_post(const float* mask_head, const float* depth_head, int batch, int h, int w, void* out_f16,
                               void* stream);
 
+/* Pyramid pooling block of the ground-segmentation network (preprocessing/segmentation/network.py:174-207,
+ * Segmentor(use_PSP=True)): for s in (1, 2, 4, 6) AdaptiveAvgPool2d(s) -> 1x1 convolution 512 -> 128 without bias ->
+ * bilinear upsample to h x w (align_corners=True), then torch.cat([x, x6, x4, x2, x1], 1).
+ *   x   NHWC 16-bit [batch][h][w][512] (encoder layer4 output)        w_pool*  fp32 [128][512], the reduce.weight parameters
+ *   out NHWC 16-bit [batch][h][w][1024], input of decoder.block1.pre_concat_conv.conv1 */
+int fp_psp_fwd(const void* x, int batch, int h, int w, int dtype, const float* w_pool1, const float* w_pool2,
+               const float* w_pool4, const float* w_pool6, void* out, void* stream);
+
+/* Input edge of the inference callers (predict_simple.py:41-43,51-60 and datasets/inference_dataset.py:25-27,45-48):
+ * `transforms.Resize((H, W), interpolation=Image.ANTIALIAS)` + `transforms.ToTensor()` on uint8 RGB frames, bit-exact with
+ * Pillow's two-pass fixed-point Lanczos resampling (Resample.c: horizontal pass into a uint8 intermediate over the source
+ * rows the vertical pass needs, then the vertical pass), fused with the /255 conversion to the float32 NCHW network input.
+ *   src    uint8 [batch][hin][win][3] (RGB, packed)           tmp  uint8 [batch][ht][wout][4] (RGBX scratch, caller-owned)
+ *   bounds int32 [out][2] = (first tap, tap count)             taps int32 [ksize][out] 22-bit fixed-point weights (tap-major)
+ * as Pillow's precompute_coeffs + normalize_coeffs_8bpc produce them for the full-image box (the host builds them once per
+ * geometry); the vertical bounds are relative to row y0 of the source, the first row the vertical pass reads. */
+int fp_resize_u8_horizontal(const void* src, int batch, int hin, int win, int y0, int ht, int wout, const int32_t* bounds,
+                            const int32_t* taps, int ksize, void* tmp, void* stream);
+int fp_resize_u8_vertical_to_f32(const void* tmp, int batch, int ht, int wout, int hout, const int32_t* bounds,
+                                 const int32_t* taps, int ksize, float* out_nchw, void* stream);
+
 /* Heads (OutConvBlock, network.py:161-183): 3x3 reflection-padded convolution Cin -> 2 (+ Sigmoid) on CUDA cores
  * (N = 2 wastes the tensor-core tile).  x: NHWC 16-bit [batch][h][w][c], c a multiple of 8 <= 128; w_oihw [2][c][3][3]
  * and bias [2] are the fp32 parameters themselves; out: fp32 [batch][h][w][2] (input of fp_heads_to_nchw). */

@@ -136,11 +136,28 @@ def network_forward(sd, image, arch='resnet34', training=False, new_stats=None, 
     return OrderedDict((k, torch.cat([mask[k], depth[k]], 1)) for k in mask)
 
 
+def psp_forward(sd, x, prefix='decoder.PSP'):
+    """PSP.forward -- footprints/preprocessing/segmentation/network.py:174-207: four PSPBlocks (adaptive average pool to
+    1/2/4/6 cells -> 1x1 conv 512->128 without bias -> bilinear upsample back, align_corners=True), concatenated behind x
+    in the order [x, x6, x4, x2, x1]."""
+    h, w = x.shape[2:]
+    levels = []
+    for i, s in ((1, 1), (2, 2), (3, 4), (4, 6)):
+        y = F.conv2d(F.adaptive_avg_pool2d(x, (s, s)), sd[f'{prefix}.block{i}.reduce.weight'])
+        levels.append(F.interpolate(y, size=(h, w), mode='bilinear', align_corners=True))
+    x1, x2, x4, x6 = levels
+    return torch.cat([x, x6, x4, x2, x1], 1)
+
+
 def segmentor_forward(sd, image, arch='resnet34', training=False):
-    """Segmentor.forward (use_PSP=False) -- footprints/preprocessing/segmentation/network.py:20-24,79-101: the same
+    """Segmentor.forward -- footprints/preprocessing/segmentation/network.py:20-24,79-101: the same
     encoder, one skip decoder, 1-channel heads (OutConvBlock :158-170: reflection pad + 3x3 conv, NO sigmoid, NO
-    upsampling).  Returns the list of four [B,1,h,w] outputs at 1/8, 1/4, 1/2 and full resolution."""
+    upsampling); the pyramid-pooling block in front of the decoder when the state dict holds its weights (use_PSP=True,
+    :63-64,82-83).  Returns the list of four [B,1,h,w] outputs at 1/8, 1/4, 1/2 and full resolution."""
     feats = encoder_forward(sd, image, arch, training)
+    if 'decoder.PSP.block1.reduce.weight' in sd:
+        feats = list(feats)
+        feats[-1] = psp_forward(sd, feats[-1])
 
     def head(p, x):
         return F.conv2d(F.pad(x, (1, 1, 1, 1), mode='reflect'), sd[f'{p}.conv1.weight'], sd[f'{p}.conv1.bias'])

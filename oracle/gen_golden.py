@@ -106,14 +106,14 @@ def run(arch, batch, height, width, tag):
           out['loss/loss'])
 
 
-def run_segmentor(batch, height, width, tag):
-    """Eval outputs of the reference's ground-segmentation network (preprocessing/segmentation/network.py, use_PSP=False)."""
+def run_segmentor(batch, height, width, tag, use_PSP=False):
+    """Eval outputs of the reference's ground-segmentation network (preprocessing/segmentation/network.py)."""
     from footprints_b200.synthetic import segmentor_state_spec
     import footprints.preprocessing.segmentation.network as sn
     sn.resnet34 = lambda pretrained=True: torchvision.models.resnet34(weights=None)
     torch.manual_seed(0)
-    net = sn.Segmentor(pretrained=False, use_PSP=False)
-    spec = segmentor_state_spec('resnet34')
+    net = sn.Segmentor(pretrained=False, use_PSP=use_PSP)
+    spec = segmentor_state_spec('resnet34', use_PSP=use_PSP)
     ref_sd = net.state_dict()
     assert list(ref_sd.keys()) == list(spec.keys()), 'segmentor state_dict key order differs from reference'
     for k in spec:
@@ -139,6 +139,8 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'segmentor':
         run_segmentor(2, 64, 96, 'ref_segmentor_b2_64x96')
         run_segmentor(1, 192, 640, 'ref_segmentor_b1_192x640')
+        run_segmentor(2, 64, 96, 'ref_segmentor_psp_b2_64x96', use_PSP=True)
+        run_segmentor(1, 192, 640, 'ref_segmentor_psp_b1_192x640', use_PSP=True)
         sys.exit(0)
     run('resnet34', 2, 64, 96, 'ref_resnet34_b2_64x96')
     run('resnet18', 2, 64, 96, 'ref_resnet18_b2_64x96')

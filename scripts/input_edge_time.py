@@ -1,0 +1,93 @@
+"""Timing of the input edge (footprints_b200.preprocess.ResizeToTensor) on KITTI-sized frames, next to Pillow on the host.
+
+    python scripts/input_edge_time.py [--batch 64] [--iters 50] > gpurun_out/input_edge.json
+
+Algorithmic bytes per frame: 375*1242*3 (uint8 source, read once) + 3*192*640*4 (float32 network input, written once)
+= 1.397 + 1.475 MB; the RGBX intermediate (246 rows * 640 * 4 B = 0.63 MB) is written and re-read through L2.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+from PIL import Image
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from footprints_b200.preprocess import ResizeToTensor  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--iters', type=int, default=50)
+    ap.add_argument('--hw-in', default='375x1242')
+    ap.add_argument('--hw-out', default='192x640')
+    a = ap.parse_args()
+    hin, win = map(int, a.hw_in.split('x'))
+    ho, wo = map(int, a.hw_out.split('x'))
+    rng = np.random.default_rng(0)
+    host = torch.from_numpy(rng.integers(0, 256, (a.batch, hin, win, 3), dtype=np.uint8)).pin_memory()
+    dev = host.cuda()
+    rt = ResizeToTensor((ho, wo))
+    for _ in range(5):
+        rt(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for _ in range(a.iters):
+        flush.zero_()                                   # L2 flush between timed iterations
+        e0.record()
+        rt(dev)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    resident = float(np.median(ms))
+    ms = []
+    for _ in range(a.iters):
+        flush.zero_()
+        e0.record()
+        rt(host)                                        # pinned uint8 frames: H2D inside the timed region
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    e2e = float(np.median(ms))
+
+    frames = [host[i].numpy() for i in range(min(a.batch, 16))]
+
+    def pillow(frame):
+        img = Image.fromarray(frame).resize((wo, ho), Image.LANCZOS)
+        return torch.from_numpy(np.asarray(img).copy()).permute(2, 0, 1).contiguous().to(torch.float32).div(255)
+
+    pillow(frames[0])
+    t = time.perf_counter()
+    for f in frames:
+        pillow(f)
+    one = (time.perf_counter() - t) / len(frames)
+    cores = os.cpu_count() or 1
+    with ThreadPoolExecutor(cores) as pool:             # Pillow releases the GIL inside resize
+        list(pool.map(pillow, frames))
+        t = time.perf_counter()
+        for _ in range(4):
+            list(pool.map(pillow, frames))
+        allc = (time.perf_counter() - t) / (4 * len(frames))
+
+    alg = hin * win * 3 + 3 * ho * wo * 4
+    peaks = {}
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        peaks = json.load(open(p))
+    print(json.dumps({
+        'what': 'input edge: Resize(ANTIALIAS) + ToTensor', 'frame': [hin, win], 'out': [ho, wo], 'batch': a.batch,
+        'gpu_resident_ms_per_batch': resident, 'gpu_resident_frames_per_s': a.batch / resident * 1e3,
+        'gpu_e2e_pinned_u8_ms_per_batch': e2e, 'gpu_e2e_frames_per_s': a.batch / e2e * 1e3,
+        'algorithmic_bytes_per_frame': alg, 'achieved_GBps': alg * a.batch / resident / 1e6,
+        'pillow_ms_per_frame_1_thread': one * 1e3, 'pillow_frames_per_s_1_thread': 1 / one,
+        'pillow_frames_per_s_all_cores': 1 / allc, 'cores': cores, 'l2_flush': True, 'measured_peaks': peaks}))
+
+
+if __name__ == '__main__':
+    main()

@@ -65,6 +65,35 @@ def test_predict_simple_runs_unmodified_over_footprints_b200(tmp_path, monkeypat
     assert err <= 1e-3
 
 
+@needs_ref
+def test_predict_simple_with_the_gpu_input_edge(tmp_path, monkeypatch):
+    """predict_simple.py:51-60 with its two host transforms replaced by footprints_b200.preprocess.ResizeToTensor: the network
+    input and the saved prediction are IDENTICAL to the run that resizes with Pillow on the host."""
+    import footprints.predict_simple as ps
+    import footprints_b200
+    from footprints_b200.preprocess import ResizeToTensor
+    _, model_dir = _reference_weights(str(tmp_path))
+    monkeypatch.setattr(ps, 'download_model_if_doesnt_exist', lambda name: None)
+    monkeypatch.setattr(ps, 'MODEL_DIR', model_dir)
+    monkeypatch.setattr(ps, 'ModelManager', functools.partial(footprints_b200.ModelManager, pretrained=False))
+    image = os.path.join(REF, 'test_data', 'cyclist.jpg')
+
+    host = ps.InferenceManager('kitti', str(tmp_path / 'host'), use_cuda=True, save_visualisations=False)
+    _, host_input = host._load_and_preprocess_image(image)
+    host.predict(image)
+
+    gpu = ps.InferenceManager('kitti', str(tmp_path / 'gpu'), use_cuda=True, save_visualisations=False)
+    gpu.resizer = lambda frame: frame                                   # predict_simple.py:41-42
+    gpu.totensor = ResizeToTensor(ps.MODEL_HEIGHT_WIDTH['kitti'])        # predict_simple.py:43
+    _, gpu_input = gpu._load_and_preprocess_image(image)
+    gpu.predict(image)
+
+    assert gpu_input.is_cuda and gpu_input.shape == host_input.shape and torch.equal(gpu_input, host_input)
+    a = np.load(str(tmp_path / 'host' / 'outputs' / 'cyclist.npy'))
+    b = np.load(str(tmp_path / 'gpu' / 'outputs' / 'cyclist.npy'))
+    assert np.array_equal(a, b)
+
+
 def _synthetic_inputs(b, h, w, seed):
     from footprints_b200.synthetic import synthetic_batch
     return synthetic_batch(b, h, w, seed)

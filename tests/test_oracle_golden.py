@@ -86,12 +86,13 @@ def test_oracle_full_resolution_eval_matches_reference():
         np.testing.assert_allclose(v.flatten()[idx].numpy(), g[f'eval/{k}/val'], rtol=1e-4, atol=2e-5)
 
 
-@pytest.mark.parametrize('tag,shape', [('ref_segmentor_b2_64x96', (2, 64, 96)), ('ref_segmentor_b1_192x640', (1, 192, 640))])
+@pytest.mark.parametrize('tag,shape', [('ref_segmentor_b2_64x96', (2, 64, 96)), ('ref_segmentor_b1_192x640', (1, 192, 640)),
+                                       ('ref_segmentor_psp_b2_64x96', (2, 64, 96)), ('ref_segmentor_psp_b1_192x640', (1, 192, 640))])
 def test_segmentor_oracle_matches_reference_fixture(tag, shape):
     """oracle.segmentor_forward against outputs of the unmodified reference Segmentor (oracle/gen_golden.py segmentor)."""
     from footprints_b200.synthetic import segmentor_state_spec
     g = np.load(os.path.join(GOLD, f'{tag}.npz'))
-    sd = synthetic_state_dict('resnet34', 0, spec=segmentor_state_spec('resnet34'))
+    sd = synthetic_state_dict('resnet34', 0, spec=segmentor_state_spec('resnet34', use_PSP='_psp_' in tag))
     with torch.no_grad():
         outs = O.segmentor_forward(sd, synthetic_batch(*shape, 1)['image'])
     assert len(outs) == 4
