@@ -11,6 +11,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 namespace fp {
 
 __device__ __forceinline__ float2 h_up2(uint32_t u, int fmt) {
@@ -376,10 +378,15 @@ constexpr int HD_SMEM_DZ = (HT_ROWS + 2) * (HT_COLS + 2) * static_cast<int>(size
 // output element; 22 % of the fp32 FMA peak with the scalar loop), HFMA2 halves the instruction count; the 18-term sums in
 // fp16 carry ~2e-3 relative error, the accuracy class of the 16-bit gradient tensors they are stored into.  G / dZ tiles
 // then hold {half2(gx, gx), half2(gy, gy)} and the weights {half2(w0[c], w0[c+1]), half2(w1[c], w1[c+1])} per channel pair.
-template <bool HM>
-__global__ void __launch_bounds__(HT_THREADS)
+// EP = 1 (default; FP_HEAD_EPI=0 selects 0): the epilogue's operands (the activation for ELU' / ReLU', the gradient to
+// accumulate into) are requested BEFORE the FMA loop of their channel block, so their DRAM latency hides behind it -- with
+// the loads after the loop the kernel spent 40-64 % of its issue slots stalled on them (ncu, profiles/r02F_head_dgrad.md) --
+// and, with fp16 activations and gradients, the epilogue stays in packed half2 (clamp, ELU' factor min(y + 1, 1), product,
+// accumulate: 2.5 instead of ~8.5 instructions per element).
+template <bool HM, int EP, bool ACC>
+__global__ void __launch_bounds__(HT_THREADS, (HM && EP) ? (ACC ? 3 : 4) : 1)
 head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ w, int H, int W, int C, int tiles_x,
-                       int tiles_y, int accumulate, const uint4* __restrict__ yact, int act, int act_fmt, int grad_fmt,
+                       int tiles_y, const uint4* __restrict__ yact, int act, int act_fmt, int grad_fmt,
                        uint4* __restrict__ dst) {
   extern __shared__ __align__(16) uint8_t hd_smem[];
   float2* G = reinterpret_cast<float2*>(hd_smem);                       // [9][16*32]
@@ -411,20 +418,21 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
       sw[i] = make_float2(w[(0 * C + c) * 9 + t], w[(1 * C + c) * 9 + t]);
     }
   }
-  // dZ halo tile (1 pixel each side, zero outside the image) staged once; every G term lies inside it
+  // tiles that hold none of the rows 1, H-2 / columns 1, W-2 have no reflected terms: G[t][p] is just dZ shifted by the
+  // tap, read straight from the halo tile (3/4 of the tiles at 192x640) -- the G table is only built for border tiles
+  const bool interior = !(ty0 <= 1) && !(ty0 <= H - 2 && H - 2 < ty0 + HT_ROWS) &&
+                        !(tx0 <= 1) && !(tx0 <= W - 2 && W - 2 < tx0 + HT_COLS);
+  // dZ halo tile (1 pixel each side, zero outside the image) staged once; every G term lies inside it.  Interior tiles of
+  // the packed loop keep it in the loop's operand form (the conversion happens once here, not per tap and channel block)
   for (int i = tid; i < (HT_ROWS + 2) * (HT_COLS + 2); i += HT_THREADS) {
     const int hy = i / (HT_COLS + 2), hx = i - hy * (HT_COLS + 2);
     const int qy = ty0 + hy - 1, qx = tx0 + hx - 1;
     float2 d = make_float2(0.f, 0.f);
     if (qy >= 0 && qy < H && qx >= 0 && qx < W)
       d = h_up2(__ldg(reinterpret_cast<const uint32_t*>(dz8 + (img * H + qy) * W + qx)), grad_fmt);
-    dzs[i] = d;
+    dzs[i] = (HM && interior) ? pack_g(d) : d;
   }
   __syncthreads();
-  // tiles that hold none of the rows 1, H-2 / columns 1, W-2 have no reflected terms: G[t][p] is just dZ shifted by the
-  // tap, read straight from the halo tile (3/4 of the tiles at 192x640) -- the G table is only built for border tiles
-  const bool interior = !(ty0 <= 1) && !(ty0 <= H - 2 && H - 2 < ty0 + HT_ROWS) &&
-                        !(tx0 <= 1) && !(tx0 <= W - 2 && W - 2 < tx0 + HT_COLS);
   for (int i = interior ? 9 * HT_ROWS * HT_COLS : tid; i < 9 * HT_ROWS * HT_COLS; i += HT_THREADS) {
     const int t = i / (HT_ROWS * HT_COLS), pix = i - t * (HT_ROWS * HT_COLS);
     const int ry = pix / HT_COLS, rx = pix - ry * HT_COLS;
@@ -457,6 +465,20 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
   const int px = tx0 + lx;
   for (int cb = 0; cb < C; cb += 16) {
     float acc[4][16];
+    uint4 pre_y[4][2], pre_d[4][2];
+    if (EP) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int py = ty0 + ly + r;
+        const bool ok = py < H && px < W;
+        const long long o = ok ? ((img * H + py) * W + px) * c8 + (cb >> 3) : 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          pre_y[r][h] = (ok && yact != nullptr) ? __ldg(&yact[o + h]) : make_uint4(0u, 0u, 0u, 0u);
+          pre_d[r][h] = (ok && ACC) ? dst[o + h] : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
     if (HM) {
       __half2 hacc[4][8];
 #pragma unroll
@@ -468,7 +490,7 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
         float2 g[4];
         if (interior) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r) g[r] = pack_g(dzs[(ly + r + 2 - t / 3) * (HT_COLS + 2) + lx + 2 - t % 3]);
+          for (int r = 0; r < 4; ++r) g[r] = dzs[(ly + r + 2 - t / 3) * (HT_COLS + 2) + lx + 2 - t % 3];
         } else {
 #pragma unroll
           for (int r = 0; r < 4; ++r) g[r] = G[t * (HT_ROWS * HT_COLS) + (ly + r) * HT_COLS + lx];
@@ -486,6 +508,36 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
                                  __hfma2(w1, *reinterpret_cast<const __half2*>(&gyb), hacc[r][i]));
           }
         }
+      }
+      if (EP && act_fmt == FP_F16) {
+        const __half2 one2 = __float2half2_rn(1.f), zero2 = __float2half2_rn(0.f);
+        const __half2 hi2 = __float2half2_rn(65504.f), lo2 = __float2half2_rn(-65504.f);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int py = ty0 + ly + r;
+          if (py >= H || px >= W) continue;
+          const long long o = ((img * H + py) * W + px) * c8 + (cb >> 3);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t yv[4] = {pre_y[r][h].x, pre_y[r][h].y, pre_y[r][h].z, pre_y[r][h].w};
+            const uint32_t dv[4] = {pre_d[r][h].x, pre_d[r][h].y, pre_d[r][h].z, pre_d[r][h].w};
+            uint32_t ov[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __half2 v = __hmin2(__hmax2(hacc[r][h * 4 + q], lo2), hi2);      // an overflowed sum (inf) clips first: inf * 0 = NaN
+              // dst holds the other consumer's gradient w.r.t. the activation: the derivative applies to the sum
+              if (ACC) v = __hmin2(__hmax2(__hadd2(v, *reinterpret_cast<const __half2*>(&dv[q])), lo2), hi2);
+              if (yact != nullptr) {
+                const __half2 y2 = *reinterpret_cast<const __half2*>(&yv[q]);
+                if (act == FP_ACT_ELU) v = __hmul2(v, __hmin2(__hadd2(y2, one2), one2));   // ELU'(y) = y > 0 ? 1 : y + 1
+                else if (act == FP_ACT_RELU) v = __hmul2(v, __hgt2(y2, zero2));
+              }
+              ov[q] = *reinterpret_cast<const uint32_t*>(&v);
+            }
+            dst[o + h] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+          }
+        }
+        continue;
       }
 #pragma unroll
       for (int r = 0; r < 4; ++r)
@@ -529,15 +581,15 @@ head_dgrad_tile_kernel(const uint4* __restrict__ dz8, const float* __restrict__ 
         float a[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = acc[r][h * 8 + i];
-        if (accumulate) {
+        if (ACC) {
           float f[8];
-          h_unpack8(dst[o + h], grad_fmt, f);
+          h_unpack8(EP ? pre_d[r][h] : dst[o + h], grad_fmt, f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) a[i] += f[i];
         }
         if (yact != nullptr) {
           float fy[8];
-          h_unpack8(__ldg(&yact[o + h]), act_fmt, fy);
+          h_unpack8(EP ? pre_y[r][h] : __ldg(&yact[o + h]), act_fmt, fy);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (act == FP_ACT_ELU) a[i] *= fy[i] > 0.f ? 1.f : fy[i] + 1.f;
@@ -765,10 +817,16 @@ extern "C" int fp_head_conv_dgrad(const void* dz8, const float* w_oihw, int batc
     const int tiles_x = (w + HT_COLS - 1) / HT_COLS, tiles_y = (h + HT_ROWS - 1) / HT_ROWS;
     const int smem = HD_SMEM_G + HD_SMEM_DZ + 9 * c * static_cast<int>(sizeof(float2));
     const bool hm = grad_dtype == FP_F16 && opts().head_hmath != 0;
-    auto kern = hm ? head_dgrad_tile_kernel<true> : head_dgrad_tile_kernel<false>;
+    const bool ep = opts().head_epi != 0;
+    auto pick = [&](auto acc) {
+      constexpr bool A = decltype(acc)::value;
+      return hm ? (ep ? head_dgrad_tile_kernel<true, 1, A> : head_dgrad_tile_kernel<true, 0, A>)
+                : (ep ? head_dgrad_tile_kernel<false, 1, A> : head_dgrad_tile_kernel<false, 0, A>);
+    };
+    auto kern = accumulate ? pick(std::true_type{}) : pick(std::false_type{});
     { const int arc = ensure_max_smem(reinterpret_cast<const void*>(kern), HD_SMEM_G + HD_SMEM_DZ + 9 * HEAD_MAX_C * static_cast<int>(sizeof(float2)), "head_dgrad_tile_kernel"); if (arc != FP_OK) return arc; }
     kern<<<static_cast<unsigned>(static_cast<long long>(batch) * tiles_x * tiles_y), HT_THREADS, smem, st>>>(
-        static_cast<const uint4*>(dz8), w_oihw, h, w, c, tiles_x, tiles_y, accumulate, static_cast<const uint4*>(y_act), act,
+        static_cast<const uint4*>(dz8), w_oihw, h, w, c, tiles_x, tiles_y, static_cast<const uint4*>(y_act), act,
         act_dtype, grad_dtype, static_cast<uint4*>(dst));
   } else if (c == 32) {
     const long long n = static_cast<long long>(batch) * h * w;

@@ -232,3 +232,49 @@ def test_rowstream_head_n16_matches_cuda_core_head_and_torch(cfg):
         assert torch.isfinite(got).all(), name
         assert (got - ref).abs().max().item() <= 5e-4, (name, (got - ref).abs().max().item())
     assert (yc.permute(0, 3, 1, 2) - outs['1']).abs().max().item() <= 5e-3      # CUDA-core kernel keeps fp32 weights
+
+
+@pytest.mark.parametrize('shape', [(2, 9, 14), (2, 37, 70)])                # one ragged tile; several tiles, ragged edges
+@pytest.mark.parametrize('C,act,accumulate', [(32, 2, 0), (64, 2, 1), (128, 1, 1), (16, 0, 0), (32, 2, 1)])
+def test_head_dgrad_epilogue_variants_match_torch(C, act, accumulate, shape):
+    """fp_head_conv_dgrad with fp16 activations and gradients (the training default): the default kernel (epilogue operands
+    prefetched before the FMA loop, packed-half epilogue), FP_HEAD_EPI=0 (loads after the loop, fp32 epilogue) and
+    FP_HEAD_HMATH=0 (fp32 FMA loop) against autograd in float64 -- with ELU' / ReLU' of the stored activation and with
+    accumulation into an existing gradient."""
+    lib = _lib.load()
+    _lib.require_device()
+    g = torch.Generator().manual_seed(C + act)
+    b, h, w = shape
+    x = torch.randn(b, C, h, w, generator=g).double().requires_grad_(True)
+    wgt = (torch.randn(2, C, 3, 3, generator=g) / (9 * C) ** 0.5).float()
+    dz = torch.randn(b, 2, h, w, generator=g).half()
+    F.conv2d(F.pad(x, (1, 1, 1, 1), mode='reflect'), wgt.double()).backward(dz.double())
+    ref = x.grad.clone()
+    old = torch.randn(b, C, h, w, generator=g).half()
+    if accumulate:                      # dst holds the other consumer's gradient w.r.t. the activation ...
+        ref = ref + old.double()
+    yact = None
+    if act:                             # ... and the activation's derivative applies to the sum
+        yact = F.elu(torch.randn(b, C, h, w, generator=g) * 1.5).half()      # a stored activation: values in (-1, ..)
+        yact[0, :, 0, :4] = -1.0                                             # saturated ELU outputs: ELU' = 0 exactly
+        yd = yact.double()
+        ref = ref * (torch.where(yd > 0, torch.ones_like(yd), yd + 1) if act == 2 else (yd > 0).double())
+    to_nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().cuda()          # noqa: E731
+    dz8 = torch.zeros(b, h, w, 8, dtype=torch.float16, device='cuda')
+    dz8[..., :2] = to_nhwc(dz)
+    y16 = to_nhwc(yact) if yact is not None else None
+    outs = {}
+    for name, env in (('default', {}), ('epi0', {'FP_HEAD_EPI': '0'}), ('fp32_loop', {'FP_HEAD_HMATH': '0'}),
+                      ('fp32_loop_epi0', {'FP_HEAD_HMATH': '0', 'FP_HEAD_EPI': '0'})):
+        with _Env(**env):
+            dx = to_nhwc(old).clone()
+            _lib.check(lib.fp_head_conv_dgrad(P(dz8), P(wgt.cuda()), b, h, w, C, accumulate, P(y16), act, 0, 0, P(dx), None))
+            torch.cuda.synchronize()
+        outs[name] = dx.permute(0, 3, 1, 2).double().cpu()
+        assert torch.isfinite(outs[name]).all()
+        err = (outs[name] - ref).abs().max().item()
+        bar = (1e-2 if 'fp32' not in name else 2e-3) * ref.abs().max().item()
+        print(f'head dgrad C={C} act={act} acc={accumulate} {shape} {name}: max abs err {err:.2e} (bar {bar:.2e})')
+        assert err <= bar, name
+    # the two fp32-loop variants differ only in where the operands are loaded
+    assert torch.equal(outs['fp32_loop'], outs['fp32_loop_epi0'])
