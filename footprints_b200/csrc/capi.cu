@@ -77,6 +77,7 @@ static void load_options() {
   o.head_tile = env_int("FP_HEAD_TILE", 1);
   o.head_hmath = env_int("FP_HEAD_HMATH", 1);
   o.head_epi = env_int("FP_HEAD_EPI", 1);
+  o.resize_rows = env_int("FP_RESIZE_ROWS", 1);
   std::lock_guard<std::mutex> lk(g_mu);
   g_opts = o;
   g_opts_loaded.store(1);

@@ -17,7 +17,7 @@ int num_sms();       // SM count of the CURRENT device (cached per device ordina
 // calls per convolution launch; fp_reload_options() re-reads them (the tests flip switches inside one process).
 struct Options {
   int strip, strip_mineff, strip_tma, strip_wres, rowstream, rowstream_mineff, a_mode, debug_flags;
-  int wgrad_strip, wgrad_roll, wgrad_fuse_taps, head_tile, head_hmath, head_epi;
+  int wgrad_strip, wgrad_roll, wgrad_fuse_taps, head_tile, head_hmath, head_epi, resize_rows;
 };
 const Options& opts();
 

@@ -170,7 +170,8 @@ int fp_psp_fwd(const void* x, int batch, int h, int w, int dtype, const float* w
  * Pillow's two-pass fixed-point Lanczos resampling (Resample.c: horizontal pass into a uint8 intermediate over the source
  * rows the vertical pass needs, then the vertical pass), fused with the /255 conversion to the float32 NCHW network input.
  *   src    uint8 [batch][hin][win][3] (RGB, packed)           tmp  uint8 [batch][ht][wout][4] (RGBX scratch, caller-owned)
- *   bounds int32 [out][2] = (first tap, tap count)             taps int32 [ksize][out] 22-bit fixed-point weights (tap-major)
+ *   bounds int32 [out][2] = (first tap, tap count)             taps int32 [ksize][out] 22-bit fixed-point weights (tap-major),
+ *                                                                   ZERO past an output's tap count (Pillow leaves them empty too)
  * as Pillow's precompute_coeffs + normalize_coeffs_8bpc produce them for the full-image box (the host builds them once per
  * geometry); the vertical bounds are relative to row y0 of the source, the first row the vertical pass reads. */
 int fp_resize_u8_horizontal(const void* src, int batch, int hin, int win, int y0, int ht, int wout, const int32_t* bounds,

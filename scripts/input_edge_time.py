@@ -40,7 +40,8 @@ def main():
     ms = []
     for _ in range(a.iters):
         flush.zero_()                                   # L2 flush between timed iterations
-        e0.record()
+        torch.cuda._sleep(3_000_000)                    # ~1.5 ms of GPU idle-spin: the host enqueues the whole call behind it,
+        e0.record()                                     # so the event interval is device time, not Python launch overhead
         rt(dev)
         e1.record()
         torch.cuda.synchronize()
@@ -49,6 +50,7 @@ def main():
     ms = []
     for _ in range(a.iters):
         flush.zero_()
+        torch.cuda._sleep(3_000_000)
         e0.record()
         rt(host)                                        # pinned uint8 frames: H2D inside the timed region
         e1.record()

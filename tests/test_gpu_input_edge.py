@@ -76,6 +76,33 @@ def test_very_wide_rows_use_the_large_shared_memory_path():
     assert torch.equal(out.cpu(), _pillow(frame, 32, 640))
 
 
+def test_wide_rows_with_few_taps_use_the_row_group_kernel_with_opt_in_shared_memory():
+    from footprints_b200.preprocess import ResizeToTensor
+    rng = np.random.default_rng(8)
+    frame = rng.integers(0, 256, (8, 13000, 3), dtype=np.uint8)         # 31 taps, 52 KB per staged RGBX row
+    out = ResizeToTensor((16, 2600))(frame)
+    assert torch.equal(out.cpu(), _pillow(frame, 16, 2600))
+
+
+@pytest.mark.parametrize('hin,win,ho,wo', [(375, 1242, 192, 640), (100, 200, 192, 640), (33, 1001, 63, 97)])
+def test_first_generation_kernels_give_the_same_bits(hin, win, ho, wo):
+    """FP_RESIZE_ROWS=0: the one-row-per-CTA / one-output-row-per-thread kernels (also the fallback for more than 32 taps)."""
+    from footprints_b200 import _lib
+    from footprints_b200.preprocess import ResizeToTensor
+    rng = np.random.default_rng(hin)
+    frames = rng.integers(0, 256, (2, hin, win, 3), dtype=np.uint8)
+    default = ResizeToTensor((ho, wo))(frames)
+    os.environ['FP_RESIZE_ROWS'] = '0'
+    _lib.load().fp_reload_options()
+    try:
+        first = ResizeToTensor((ho, wo))(frames)
+    finally:
+        os.environ.pop('FP_RESIZE_ROWS')
+        _lib.load().fp_reload_options()
+    assert torch.equal(default, first)
+    assert torch.equal(default[1].cpu(), _pillow(frames[1], ho, wo))
+
+
 def test_bad_inputs_raise():
     from footprints_b200.preprocess import ResizeToTensor
     rt = ResizeToTensor((64, 96))
