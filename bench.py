@@ -304,6 +304,41 @@ def main():
     ms_e2e = timed(step_e2e, args.steps) / args.steps
     e2e_value = world * B / (ms_e2e * 1e-3)
 
+    # ---- inference only: the caller's whole loop (evaluation/inference.py:95-110) with BOTH edges on the GPU: pinned uint8
+    # camera frames -> H2D -> ResizeToTensor (Pillow-exact Lanczos + ToTensor) -> network -> sigmoid + float16 -> D2H
+    e2e_frames = None
+    if args.mode == 'infer' and world == 1:
+        from footprints_b200.preprocess import ResizeToTensor
+        fh, fw = (375, 1242) if (H, W) == (192, 640) else (2 * H, 2 * W)
+        frames_host = torch.randint(0, 256, (B, fh, fw, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).pin_memory()
+        fbufs = [torch.empty((B, fh, fw, 3), dtype=torch.uint8, device=bufs[0]['image'].device) for _ in range(2)]
+        resize = ResizeToTensor((H, W))
+        out16 = torch.empty((B, 4, H, W), dtype=torch.float16).pin_memory()
+
+        def upload_frames(i):
+            with torch.cuda.stream(copy_stream):
+                fbufs[i].copy_(frames_host, non_blocking=True)
+                ready[i].record(copy_stream)
+
+        def step_frames():
+            i = state['i']
+            torch.cuda.current_stream().wait_event(ready[i])
+            upload_frames(1 - i)
+            out16.copy_(net.predict_for_saving(resize(fbufs[i])), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            state['i'] = 1 - i
+
+        torch.cuda.synchronize()
+        state['i'] = 0
+        upload_frames(0)
+        for _ in range(2):
+            step_frames()
+        ms_frames = timed(step_frames, args.steps) / args.steps
+        e2e_frames = {'value': B / (ms_frames * 1e-3), 'unit': 'images/s', 'ms_per_step': ms_frames,
+                      'h2d_bytes_per_step': frames_host.numel(), 'd2h_bytes_per_step': out16.numel() * 2,
+                      'what': f'pinned uint8 {fh}x{fw} frames -> ResizeToTensor -> forward -> sigmoid + float16 [B,4,{H},{W}] read back'}
+
     # ---- roofline of the dominant kernel class (tcgen05 implicit-GEMM conv: forward + data-gradient launches)
     roofline = None
     # every rank runs the instrumented step (it contains the gradient all-reduce); only rank 0 records events
@@ -441,6 +476,8 @@ def main():
         line['config']['precise'] = bool(args.precise)
         line['config']['cuda_graph'] = bool(args.mode == 'train' and not args.no_graph)
         line.update(extra)
+        if e2e_frames is not None:
+            line['e2e_from_uint8_frames'] = e2e_frames
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
