@@ -70,3 +70,60 @@ def test_resize_has_no_cpu_fallback():
     from footprints_b200.preprocess import ResizeToTensor
     with pytest.raises(RuntimeError):
         ResizeToTensor((192, 640), device='cpu')
+
+
+def _model_of_the_row_group_kernels(frame, ho, wo):
+    """Python model of the ADDRESSING of the default CUDA kernels (csrc/input_edge.cu), not of Pillow: rows of a CTA staged back to
+    back with KS zero words behind the last one and KS unconditional taps per output (weights past an output's tap count are
+    zero, so a tap may read the next row's pixels); two output rows per thread fed from the union of their source rows through
+    zero-padded weight pairs.  If this model reproduces the oracle, those shortcuts are exact."""
+    from footprints_b200.preprocess import tap_table
+    hin, win = frame.shape[:2]
+    ks, bh, th = tap_table(win, wo)
+    kv, bv, tv = tap_table(hin, ho)
+    y0, y1 = int(bv[0, 0]), int(bv[-1, 0] + bv[-1, 1])
+    ht = y1 - y0
+    bv = bv.copy()
+    bv[:, 0] -= y0
+    half = 1 << (oracle.PRECISION_BITS - 1)
+    clip = lambda a: np.clip(a.astype(np.int32) >> oracle.PRECISION_BITS, 0, 255).astype(np.uint8)      # noqa: E731
+    tmp = np.zeros((ht, wo, 3), np.uint8)
+    rows_per_cta = 6
+    for r0 in range(0, ht, rows_per_cta):
+        nr = min(rows_per_cta, ht - r0)
+        flat = np.zeros((nr * win + ks, 3), np.int64)
+        flat[:nr * win] = frame[y0 + r0:y0 + r0 + nr].reshape(-1, 3)
+        for xo in range(wo):
+            for r in range(nr):
+                acc = np.full(3, half, np.int64)
+                for t in range(ks):
+                    acc += flat[r * win + bh[xo, 0] + t] * int(th[t, xo])
+                tmp[r0 + r, xo] = clip(acc)
+    out = np.zeros((ho, wo, 3), np.uint8)
+    for yo0 in range(0, ho, 2):
+        two = yo0 + 1 < ho
+        first0, n0 = int(bv[yo0, 0]), int(bv[yo0, 1])
+        first1, n1 = (int(bv[yo0 + 1, 0]), int(bv[yo0 + 1, 1])) if two else (first0, 0)
+        shift = first1 - first0
+        assert shift >= 0
+        span = max(n0, shift + n1)
+        assert span <= 64 and first0 + span <= ht
+        a0 = np.full((wo, 3), half, np.int64)
+        a1 = a0.copy()
+        for j in range(span):
+            k0 = int(tv[j, yo0]) if j < n0 else 0
+            k1 = int(tv[j - shift, yo0 + 1]) if 0 <= j - shift < n1 else 0
+            v = tmp[first0 + j].astype(np.int64)
+            a0 += v * k0
+            a1 += v * k1
+        out[yo0] = clip(a0)
+        if two:
+            out[yo0 + 1] = clip(a1)
+    return out
+
+
+@pytest.mark.parametrize('hin,win,ho,wo', [(37, 53, 32, 64), (20, 30, 13, 17), (50, 41, 33, 64), (12, 20, 25, 7), (9, 9, 9, 9)])
+def test_row_group_kernel_addressing_is_exact(hin, win, ho, wo):
+    rng = np.random.default_rng(hin + wo)
+    frame = rng.integers(0, 256, (hin, win, 3), dtype=np.uint8)
+    assert np.array_equal(_model_of_the_row_group_kernels(frame, ho, wo), oracle.resize_lanczos_u8(frame, (ho, wo)))
